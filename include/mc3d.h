@@ -1,0 +1,187 @@
+/*
+ * mc3d.h -- C ABI of libmc3d.so: the B200-native photon random walk behind monte_carloMPI's Python driver.
+ *
+ * The reference (amschne/monte_carloMPI) is 100 % Python and has no FFI of its own; its hot path is the inline
+ * method MonteCarlo.monte_carlo3D (monte_carloMPI/monte_carlo3D.py:1111-1490) driven by the loop at
+ * monte_carlo3D.py:1613-1616, bracketed by the mpi4py scatter / gather in monte_carloMPI/parallelize.py:19,36.
+ * This header is the boundary a maintainer binds with ctypes/cffi to replace exactly that loop (see
+ * INTEGRATION.md for the stub).  Each entry point cites the reference code it replaces.
+ *
+ * Conventions
+ *   - plain C, no torch / C++ types; every buffer is caller-allocated and C-contiguous; the library never keeps
+ *     a caller pointer after a call returns;
+ *   - every function returns 0 on success and a negative MC3D_E* code on failure; mc3d_last_error() returns a
+ *     thread-local, library-owned, NUL-terminated description of the last failure on the calling thread;
+ *   - all calls are synchronous unless they say otherwise (ctypes releases the GIL around them);
+ *   - there is no CPU fallback: without a CUDA device mc3d_create* fails with MC3D_ENODEVICE.
+ */
+#ifndef MC3D_H_
+#define MC3D_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MC3D_ABI_VERSION 1
+
+/* error codes */
+#define MC3D_OK 0
+#define MC3D_EINVAL (-1)    /* bad argument                                  */
+#define MC3D_ENODEVICE (-2) /* no usable CUDA device                         */
+#define MC3D_ECUDA (-3)     /* a CUDA runtime call failed                    */
+#define MC3D_ENCCL (-4)     /* NCCL missing or an NCCL call failed           */
+#define MC3D_ENOMEM (-5)    /* host or device allocation failed              */
+#define MC3D_ESTREAM (-6)   /* replay: recorded stream exhausted / malformed */
+
+/* mc3d_params.flags */
+#define MC3D_FLAG_LAMBERT_BOTTOM 1u  /* run(Lambertian_bottom=True), monte_carlo3D.py:1421-1428, 1452-1459   */
+#define MC3D_FLAG_LAMBERT_SURFACE 2u /* run(Lambertian_surface=True), monte_carlo3D.py:1228-1229, 1385-1387 */
+
+/* photon outcome codes, monte_carlo3D.py:1390-1466 (README.md:62-66; 5 is undocumented there) */
+#define MC3D_COND_REFLECTED 1
+#define MC3D_COND_DIFFUSE_TRANSMITTED 2
+#define MC3D_COND_DIRECT_TRANSMITTED 3
+#define MC3D_COND_ABSORBED_ICE 4
+#define MC3D_COND_ABSORBED_IMPURITY 5
+#define MC3D_N_COND 8 /* tally stride per wavelength row: index = condition, 0 = total launched, 6..7 unused */
+
+typedef struct mc3d_ctx mc3d_ctx; /* opaque; one per process (or several); not thread-safe per context */
+
+/* Scalars of one MonteCarlo.run call (monte_carlo3D.py:1492-1521 and config.ini). */
+typedef struct mc3d_params {
+    double theta0_rad;   /* self.theta_0 = pi * theta_0 / 180, monte_carlo3D.py:1508                       */
+    double tau_tot;      /* snow optical depth, config.ini:5                                               */
+    double rho_snw;      /* snow density [kg m-3], config.ini:11 (path lengths in metres)                  */
+    double r_lambert;    /* Lambertian_reflectance, monte_carlo3D.py:1506                                  */
+    double wvl0_um;      /* centre wavelength [um], monte_carlo3D.py:1519                                  */
+    double sigma_um;     /* half_width / 2.355, monte_carlo3D.py:1516                                      */
+    int32_t k_first;     /* table row r holds wavelength (k_first + r) / 100 um (np.around(.., 2) grid)     */
+    uint32_t flags;      /* MC3D_FLAG_*                                                                    */
+    int32_t n_theta_bins;/* BRF zenith bins over [0, pi/2] (post_processing.py:73-76, 435-444); 0 = none   */
+    int32_t reserved;
+} mc3d_params;
+
+/* One row of the per-wavelength SSP table, the de-duplicated form of the per-photon arrays the reference
+ * builds at monte_carlo3D.py:1524-1588, 1612 (one row per distinct rounded wavelength). */
+typedef struct mc3d_ssp_row {
+    double wvl_um;      /* rounded wavelength of this row                                                   */
+    double ssa_ice;     /* self.ssa_ice[p]                                                                  */
+    double ssa_imp;     /* self.ssa_imp[p]                                                                  */
+    double g;           /* self.g[p], Henyey-Greenstein asymmetry                                           */
+    double ext_cff_mss; /* self.ext_cff_mss[p] = ext_ice (1 - c) + ext_imp c   [m2 kg-1]                    */
+    double p_ext_imp;   /* self.P_ext_imp[p]                                                                */
+} mc3d_ssp_row;
+
+/* Per-photon outcome records, struct of arrays, index = photon id - photon_begin.  Any pointer may be NULL
+ * (that column is then not copied back).  Replaces the list of tuples returned through comm.gather
+ * (monte_carlo3D.py:1487-1488, 1618); wvn and snow_depth are table[wvl_row].  */
+typedef struct mc3d_records {
+    uint8_t *condition;  /* 1..5                                                                           */
+    int16_t *wvl_row;    /* row of the SSP table                                                            */
+    float *theta_n;      /* arccos(muz), [0, pi]                                                            */
+    float *phi_n;        /* [0, 2 pi), 0 for an unscattered photon                                          */
+    uint32_t *n_scat;    /* i - 1                                                                           */
+    float *path_length;  /* metres inside the slab                                                          */
+} mc3d_records;
+
+/* Same, fp64, for replay mode (bit-for-bit comparable with the reference's tuples). */
+typedef struct mc3d_records_f64 {
+    int32_t *condition;
+    double *wvn;
+    double *theta_n;
+    double *phi_n;
+    int64_t *n_scat;
+    double *path_length;
+    double *snow_depth;
+    int64_t *consumed;   /* stream values the photon consumed (must equal offsets[p+1] - offsets[p])          */
+} mc3d_records_f64;
+
+typedef struct mc3d_stats {
+    uint64_t n_photon;    /* photons walked by this context in the call                                     */
+    uint64_t n_events;    /* sum over photons of (n_scat + 1) = loop iterations of monte_carlo3D.py:1212      */
+    double kernel_ms;     /* CUDA-event time of the walk kernel(s), max over this context's devices         */
+    double total_ms;      /* host wall time of the call (uploads + kernel + copy-back + reduce)             */
+    int32_t n_devices;
+    int32_t sm_count;     /* of device 0 of the context                                                     */
+    int32_t sm_clock_khz; /* cudaDevAttrClockRate of device 0                                               */
+    int32_t grid_blocks;  /* persistent blocks launched per device                                          */
+    int32_t block_threads;
+    int32_t reserved;
+} mc3d_stats;
+
+/* ---- library / device discovery ---------------------------------------------------------------------- */
+int mc3d_abi_version(void);
+const char *mc3d_last_error(void);
+/* Number of CUDA devices and properties of device `device` (any out pointer may be NULL). */
+int mc3d_query(int device, int *n_devices, int *sm_count, int *sm_clock_khz, uint64_t *global_mem_bytes,
+               int *cc_major, int *cc_minor);
+
+/* ---- contexts (replace `Parallel(...)`'s MPI.COMM_WORLD, parallelize.py:6-12) ------------------------- */
+/* Single process driving n_dev devices (n_dev >= 1).  With n_dev > 1 a NCCL communicator is created with
+ * ncclCommInitAll; photon-id ranges follow np.array_split (parallelize.py:14-15). */
+int mc3d_create(mc3d_ctx **ctx, const int *device_ids, int n_dev);
+/* One process per GPU (torchrun / mpirun style): rank 0 calls mc3d_nccl_unique_id, ships the 128 bytes to all
+ * ranks by any means, every rank calls mc3d_create_rank.  world_size == 1 needs no id (may be NULL). */
+int mc3d_nccl_unique_id(uint8_t id_out[128]);
+int mc3d_create_rank(mc3d_ctx **ctx, int device_id, const uint8_t nccl_id[128], int rank, int world_size);
+int mc3d_destroy(mc3d_ctx *ctx);
+
+/* ---- pinned host memory for the record arrays (so copy-back runs at PCIe speed) ------------------------ */
+int mc3d_host_alloc(void **ptr, uint64_t bytes);
+int mc3d_host_free(void *ptr);
+
+/* ---- the hot path --------------------------------------------------------------------------------------
+ * Production mode (fp32 walk, Philox4x32-10 keyed on (seed, photon id)).  Walks photon ids
+ * [photon_begin, photon_begin + n_photon) -- replaces the loop monte_carlo3D.py:1613-1616 together with
+ * initial_pdfs/populate_pdfs (monte_carlo3D.py:885-921, 1010-1044), Henyey_Greenstein2 (790-800) and the
+ * per-photon wavelength draw (1515-1520).  In a multi-device context the range is split with np.array_split
+ * boundaries; in a multi-rank context each rank passes its own sub-range.
+ *
+ *   table, n_rows   per-wavelength SSP rows; photons whose drawn wavelength falls outside are clamped to the
+ *                   first / last row (cannot happen for a table covering +-7 sigma: |z| <= 6.8 with 32-bit
+ *                   uniforms).
+ *   records         NULL, or SoA destination for this call's photons (host memory, ideally mc3d_host_alloc'd).
+ *   tally           NULL, or uint64[n_rows * (MC3D_N_COND + n_theta_bins)]: per row, outcome counts by
+ *                   condition followed by the reflected-photon zenith histogram (np.histogram semantics of
+ *                   post_processing.py:73-76 applied to float64(theta_n)).  OVERWRITTEN with this call's
+ *                   counts, reduced over all devices of the context; in a multi-rank context call
+ *                   mc3d_reduce_tally afterwards for the job total.
+ */
+int mc3d_run(mc3d_ctx *ctx, const mc3d_params *params, const mc3d_ssp_row *table, int n_rows, uint64_t seed,
+             uint64_t photon_begin, uint64_t n_photon, const mc3d_records *records, uint64_t *tally,
+             mc3d_stats *stats);
+
+/* Asynchronous variant: enqueues upload + walk + copy-back on the context's streams and returns; the record
+ * and tally buffers must stay valid (and should be pinned) until mc3d_wait.  `slot` (0 or 1) selects one of two
+ * independent device buffer sets so that two calls can be in flight (copy-back of one overlaps the walk of the
+ * next).  mc3d_wait(ctx, slot, stats) blocks until that slot is complete. */
+int mc3d_run_async(mc3d_ctx *ctx, int slot, const mc3d_params *params, const mc3d_ssp_row *table, int n_rows,
+                   uint64_t seed, uint64_t photon_begin, uint64_t n_photon, const mc3d_records *records,
+                   uint64_t *tally, mc3d_stats *stats);
+int mc3d_wait(mc3d_ctx *ctx, int slot, mc3d_stats *stats);
+
+/* Sum `tally` (uint64[n]) over the ranks of a multi-rank context with one ncclReduce to `root`
+ * (replaces comm.gather for the reduced quantities, parallelize.py:19).  In place; no-op for world_size 1. */
+int mc3d_reduce_tally(mc3d_ctx *ctx, uint64_t *tally, uint64_t n, int root);
+
+/* Replay mode (fp64 walk that consumes the reference's own recorded random stream; correctness tool).
+ * Per-photon inputs are the arrays the reference holds at monte_carlo3D.py:1575-1612: wvl, ssa_ice, ssa_imp,
+ * g, ext_cff_mss, P_ext_imp (each double[n_photon]); init_draws = the 3 uniforms per photon of initial_pdfs
+ * (monte_carlo3D.py:1035-1038); stream/offsets = raw uniforms consumed by photon p's walk in order
+ * [r1, u_phi, u_tau, u_ssa, u_ext [, u_refl] [, (u_theta, r)...]]* , stream[offsets[p] .. offsets[p+1]).
+ * n_mismatch receives the number of photons whose consumed count differs from the recorded one. */
+int mc3d_replay(mc3d_ctx *ctx, const mc3d_params *params, uint64_t n_photon, const double *wvl,
+                const double *ssa_ice, const double *ssa_imp, const double *g, const double *ext_cff_mss,
+                const double *p_ext_imp, const double *init_draws, const int64_t *offsets, const double *stream,
+                const mc3d_records_f64 *out, uint64_t *n_mismatch);
+
+/* Tuning knobs (optional; defaults are chosen from the device): persistent blocks per SM, threads per block and
+ * the idle-lane count at which a warp refills.  0 keeps the current value. */
+int mc3d_set_launch(mc3d_ctx *ctx, int blocks_per_sm, int block_threads, int refill_threshold);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MC3D_H_ */
