@@ -1,0 +1,106 @@
+// finalize_kernel.cu -- turns the walk kernel's raw per-photon results into the reference's output columns and
+// the outcome / BRF tallies.  One thread per photon, fully coalesced, HBM-trivial (32 B in, <= 19 B out).
+//
+// Reference lines reproduced here:
+//   theta_n = arccos(muz_0), phi_n by quadrant (== atan2 wrapped to [0, 2 pi)), 0 for an unscattered photon
+//                                                              monte_carloMPI/monte_carlo3D.py:1468-1485
+//   path_length [m] = sum dtau / (ext_cff_mss rho_snw)        monte_carlo3D.py:1355-1356, 1372
+//   outcome tallies by condition (calculate_albedo)           monte_carlo3D.py:1659-1671
+//   BRF zenith histogram of reflected photons, np.histogram(theta, bins=n, range=(0, pi/2))
+//                                                              post_processing.py:73-76
+// Tallies are integer counts per wavelength row (the wvn weights of the reference are applied on the host in
+// fp64), so they are exact and independent of the order of accumulation and of the GPU count.
+#include "mc3d_device.cuh"
+
+namespace mc3d {
+
+// numpy/lib/_histograms_impl.py, uniform-bin fast path, applied to float64(theta_f32)
+__device__ __forceinline__ int histogram_bin(double x, int n_bins, const double *__restrict__ edges)
+{
+    const double first = edges[0], last = edges[n_bins];
+    if (!(x >= first && x <= last)) return -1;
+    const double f = __dmul_rn(__ddiv_rn(__dsub_rn(x, first), __dsub_rn(last, first)), (double)n_bins);
+    int idx = (int)f;
+    if (idx == n_bins) idx -= 1;
+    if (x < edges[idx]) idx -= 1;
+    else if (x >= edges[idx + 1] && idx != n_bins - 1) idx += 1;
+    return idx;
+}
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) finalize_kernel(const __grid_constant__ FinalizeParams P)
+{
+    extern __shared__ unsigned int hist[];   // [n_rows][N_COND + n_theta_bins] when use_smem
+    const int stride = N_COND + P.n_theta_bins;
+    const int hist_len = P.n_rows * stride;
+    const bool tally = P.tally != nullptr;
+    if (tally && P.use_smem) {
+        for (int k = threadIdx.x; k < hist_len; k += BLOCK) hist[k] = 0u;
+        __syncthreads();
+    }
+    unsigned long long events = 0ull;
+    for (uint32_t p = blockIdx.x * BLOCK + threadIdx.x; p < P.n_photon; p += gridDim.x * BLOCK) {
+        const RawResult *src = P.raw + p;
+        const float4 a = *reinterpret_cast<const float4 *>(src);
+        const uint2 b = *reinterpret_cast<const uint2 *>(&src->n_scat);
+        const uint32_t cond = b.y & 0xffu, row = b.y >> 8;
+        const float theta = atan2f(sqrtf(fmaf(a.x, a.x, a.y * a.y)), a.z);
+        float phi = 0.0f;
+        if (b.x != 0u) {
+            phi = atan2f(a.y, a.x);
+            if (phi < 0.0f) phi += 6.283185307179586f;
+        }
+        if (P.condition) P.condition[p] = (uint8_t)cond;
+        if (P.wvl_row) P.wvl_row[p] = (int16_t)row;
+        if (P.theta_n) P.theta_n[p] = theta;
+        if (P.phi_n) P.phi_n[p] = phi;
+        if (P.n_scat) P.n_scat[p] = b.x;
+        if (P.path_length) P.path_length[p] = a.w * P.rows[row].inv_ext;
+        events += (unsigned long long)b.x + 1ull;
+        if (tally) {
+            const int base = (int)row * stride;
+            int bin = -1;
+            if (cond == 1u && P.n_theta_bins > 0) bin = histogram_bin((double)theta, P.n_theta_bins, P.edges);
+            if (P.use_smem) {
+                atomicAdd(&hist[base], 1u);
+                atomicAdd(&hist[base + cond], 1u);
+                if (bin >= 0) atomicAdd(&hist[base + N_COND + bin], 1u);
+            } else {
+                atomicAdd(&P.tally[base], 1ull);
+                atomicAdd(&P.tally[base + cond], 1ull);
+                if (bin >= 0) atomicAdd(&P.tally[base + N_COND + bin], 1ull);
+            }
+        }
+    }
+    // events: warp reduce, one atomic per warp
+    for (int o = 16; o > 0; o >>= 1) events += __shfl_xor_sync(0xffffffffu, events, o);
+    if ((threadIdx.x & 31) == 0 && events) atomicAdd(P.n_events, events);
+    if (tally && P.use_smem) {
+        __syncthreads();
+        for (int k = threadIdx.x; k < hist_len; k += BLOCK) {
+            const unsigned int v = hist[k];
+            if (v) atomicAdd(&P.tally[k], (unsigned long long)v);
+        }
+    }
+}
+
+cudaError_t launch_finalize(const FinalizeParams &P, int sm_count, cudaStream_t stream)
+{
+    constexpr int BLOCK = 256;
+    FinalizeParams Q = P;
+    const size_t hist_bytes = (size_t)P.n_rows * (N_COND + P.n_theta_bins) * sizeof(unsigned int);
+    Q.use_smem = (P.tally != nullptr && hist_bytes <= 96 * 1024) ? 1 : 0;
+    const size_t smem = Q.use_smem ? hist_bytes : 0;
+    auto kern = finalize_kernel<BLOCK>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    long long want = ((long long)P.n_photon + BLOCK - 1) / BLOCK;
+    const int per_sm = smem > 56 * 1024 ? 2 : 4;
+    int grid = (int)(want < (long long)sm_count * per_sm ? (want > 0 ? want : 1) : (long long)sm_count * per_sm);
+    kern<<<grid, BLOCK, smem, stream>>>(Q);
+    return cudaGetLastError();
+}
+
+}  // namespace mc3d

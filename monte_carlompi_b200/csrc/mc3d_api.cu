@@ -1,0 +1,778 @@
+// mc3d_api.cu -- host runtime and C ABI of libmc3d.so (see include/mc3d.h for the contract).
+//
+// What the reference does around the walk and what replaces it here:
+//   Parallel._map / np.array_split + comm.scatter   (parallelize.py:14-15, 28-38)  -> photon-id ranges per device
+//   the Python photon loop                          (monte_carlo3D.py:1613-1616)   -> walk_kernel + finalize_kernel
+//   comm.gather of per-photon tuples                (parallelize.py:19)            -> each device copies its id
+//                                                       range straight into the caller's SoA arrays
+//   (no reference equivalent) outcome / BRF tallies                               -> integer tallies, one
+//                                                       ncclReduce(sum, uint64) over NVLink when > 1 device/rank
+// NCCL is resolved with dlopen at first multi-GPU use, so the library loads (and single-GPU runs work) on hosts
+// without NCCL and shares the process' NCCL when the caller already loaded one.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <dlfcn.h>
+#include <new>
+#include <string>
+#include <vector>
+
+#include <nccl.h>
+
+#include "../../include/mc3d.h"
+#include "mc3d_device.cuh"
+
+namespace mc3d {
+cudaError_t launch_walk(const WalkParams &P, bool impurity, int block_threads, int blocks_per_sm, int grid,
+                        cudaStream_t stream);
+int walk_occupancy(bool impurity, int block_threads, int blocks_per_sm, int n_rows);
+cudaError_t launch_finalize(const FinalizeParams &P, int sm_count, cudaStream_t stream);
+cudaError_t launch_replay(const ReplayParams &P, cudaStream_t stream);
+}  // namespace mc3d
+
+using namespace mc3d;
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                                    \
+    do {                                                                                                    \
+        cudaError_t e_ = (expr);                                                                            \
+        if (e_ != cudaSuccess)                                                                              \
+            return fail(MC3D_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------ NCCL (dlopen)
+namespace {
+struct NcclApi {
+    void *handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Reduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi g_nccl;
+
+int load_nccl()
+{
+    if (g_nccl.handle) return MC3D_OK;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    void *h = nullptr;
+    for (const char *n : names) {
+        h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) return fail(MC3D_ENCCL, "NCCL not found (dlopen libnccl.so.2: %s)", dlerror());
+#define SYM(field, name)                                                        \
+    *(void **)(&g_nccl.field) = dlsym(h, name);                                 \
+    if (!g_nccl.field) return fail(MC3D_ENCCL, "NCCL symbol %s missing", name)
+    SYM(GetUniqueId, "ncclGetUniqueId");
+    SYM(CommInitRank, "ncclCommInitRank");
+    SYM(CommInitAll, "ncclCommInitAll");
+    SYM(CommDestroy, "ncclCommDestroy");
+    SYM(Reduce, "ncclReduce");
+    SYM(GroupStart, "ncclGroupStart");
+    SYM(GroupEnd, "ncclGroupEnd");
+    SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+    g_nccl.handle = h;
+    return MC3D_OK;
+}
+}  // namespace
+
+#define NCCL_TRY(expr)                                                                                       \
+    do {                                                                                                       \
+        ncclResult_t r_ = (expr);                                                                              \
+        if (r_ != ncclSuccess)                                                                                 \
+            return fail(MC3D_ENCCL, "%s failed: %s (%s:%d)", #expr, g_nccl.GetErrorString(r_), __FILE__, __LINE__); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------ context
+namespace {
+
+constexpr uint64_t CHUNK_PHOTONS = 1ull << 26;   // raw results: 32 B/photon -> 2 GiB per chunk buffer
+constexpr int N_SLOTS = 2;
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;   // elements
+    cudaError_t ensure(size_t n)
+    {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc((void **)&p, n * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct Slot {
+    DevBuf<DevRow> rows;
+    DevBuf<double> edges;
+    DevBuf<uint32_t> counters;              // one per chunk
+    DevBuf<RawResult> raw;
+    DevBuf<uint8_t> condition;
+    DevBuf<int16_t> wvl_row;
+    DevBuf<float> theta_n, phi_n, path_length;
+    DevBuf<uint32_t> n_scat;
+    DevBuf<unsigned long long> tally;       // + 1 trailing element: n_events
+    unsigned long long *host_tally = nullptr;   // pinned mirror of `tally`
+    size_t host_tally_cap = 0;
+    DevRow *host_rows = nullptr;            // pinned staging for the row upload
+    double *host_edges = nullptr;
+    size_t host_rows_cap = 0, host_edges_cap = 0;
+    std::vector<cudaEvent_t> ev;            // pairs (begin, end) around walk+finalize of each chunk
+    // pending call
+    bool busy = false;
+    uint64_t n_photon = 0;
+    size_t tally_len = 0;
+    int n_chunks = 0;
+    uint64_t *user_tally = nullptr;
+};
+
+struct Device {
+    int id = 0;
+    int sm_count = 0, clock_khz = 0;
+    cudaStream_t stream = nullptr;
+    Slot slot[N_SLOTS];
+};
+
+}  // namespace
+
+struct mc3d_ctx {
+    std::vector<Device> devs;
+    std::vector<ncclComm_t> comms;   // one per device (single process) or one (multi rank)
+    int rank = 0, world = 1;
+    int blocks_per_sm = 4, block_threads = 256, refill_threshold = 4;
+    std::chrono::steady_clock::time_point t0[N_SLOTS];
+    mc3d_stats pending_stats[N_SLOTS];
+};
+
+// ------------------------------------------------------------------------------------------------ helpers
+static void array_split(uint64_t n, int parts, int k, uint64_t *begin, uint64_t *count)
+{
+    // np.array_split boundaries (parallelize.py:14-15): the first n % parts chunks get one extra element
+    const uint64_t q = n / parts, r = n % parts;
+    *begin = (uint64_t)k * q + std::min<uint64_t>(k, r);
+    *count = q + ((uint64_t)k < r ? 1 : 0);
+}
+
+static void threshold40(double ssa, uint32_t *hi, uint32_t *lo)
+{
+    // absorbed iff (K + 1/2) 2^-40 >= ssa  <=>  K >= ceil(ssa 2^40 - 1/2)
+    double t = std::ceil(std::ldexp(ssa, 40) - 0.5);
+    if (!(t > 0.0)) t = 0.0;   // also catches NaN
+    if (t >= 1099511627776.0) { *hi = 0xffffffffu; *lo = 256u; return; }
+    const uint64_t T = (uint64_t)t;
+    *hi = (uint32_t)(T >> 8);
+    *lo = (uint32_t)(T & 0xffu);
+}
+
+static bool build_rows(const mc3d_params *P, const mc3d_ssp_row *table, int n_rows, DevRow *out)
+{
+    bool impurity = false;
+    for (int r = 0; r < n_rows; ++r) {
+        const mc3d_ssp_row &s = table[r];
+        DevRow &d = out[r];
+        d.one_m_g = (float)(1.0 - s.g);
+        d.one_m_g2 = (float)(1.0 - s.g * s.g);
+        d.two_g = (float)(2.0 * s.g);
+        d.flip = (s.g == 0.0) ? 0xffffffffu : 0u;
+        threshold40(s.ssa_ice, &d.t_hi, &d.t_lo);
+        threshold40(s.ssa_imp, &d.ti_hi, &d.ti_lo);
+        // impurity iff (w + 1/2) 2^-32 <= P_ext_imp  <=>  w <= floor(P 2^32 - 1/2)
+        const double sl = std::floor(std::ldexp(s.p_ext_imp, 32) - 0.5);
+        if (sl >= 0.0) {
+            d.s_any = 1u;
+            d.s_last = sl >= 4294967295.0 ? 0xffffffffu : (uint32_t)sl;
+            impurity = true;
+        } else {
+            d.s_any = 0u;
+            d.s_last = 0u;
+        }
+        d.inv_ext = (float)(1.0 / (s.ext_cff_mss * P->rho_snw));
+        d.pad = 0.0f;
+    }
+    return impurity;
+}
+
+static void philox_round_keys(uint64_t seed, uint32_t rk[20])
+{
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) {
+        rk[2 * r] = k0;
+        rk[2 * r + 1] = k1;
+        k0 += PHILOX_W0;
+        k1 += PHILOX_W1;
+    }
+}
+
+static int check_ctx(mc3d_ctx *ctx)
+{
+    if (!ctx || ctx->devs.empty()) return fail(MC3D_EINVAL, "null or empty context");
+    return MC3D_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ C ABI
+extern "C" {
+
+int mc3d_abi_version(void) { return MC3D_ABI_VERSION; }
+
+const char *mc3d_last_error(void) { return g_err; }
+
+int mc3d_query(int device, int *n_devices, int *sm_count, int *sm_clock_khz, uint64_t *global_mem_bytes,
+               int *cc_major, int *cc_minor)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        if (n_devices) *n_devices = 0;
+        return fail(MC3D_ENODEVICE, "no CUDA device: %s", cudaGetErrorString(e));
+    }
+    if (n_devices) *n_devices = n;
+    if (device < 0 || device >= n) return fail(MC3D_EINVAL, "device %d out of range [0, %d)", device, n);
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    int clock = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&clock, cudaDevAttrClockRate, device));
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (sm_clock_khz) *sm_clock_khz = clock;
+    if (global_mem_bytes) *global_mem_bytes = (uint64_t)prop.totalGlobalMem;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    return MC3D_OK;
+}
+
+static int init_device(Device &d, int id)
+{
+    d.id = id;
+    CUDA_TRY(cudaSetDevice(id));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, id));
+    if (prop.major < 10)
+        return fail(MC3D_ENODEVICE, "device %d is sm_%d%d; libmc3d is built for sm_100a (B200) only", id, prop.major,
+                    prop.minor);
+    d.sm_count = prop.multiProcessorCount;
+    CUDA_TRY(cudaDeviceGetAttribute(&d.clock_khz, cudaDevAttrClockRate, id));
+    CUDA_TRY(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+    return MC3D_OK;
+}
+
+int mc3d_create(mc3d_ctx **out, const int *device_ids, int n_dev)
+{
+    if (!out) return fail(MC3D_EINVAL, "ctx out pointer is null");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) return fail(MC3D_ENODEVICE, "no CUDA device: %s", cudaGetErrorString(e));
+    if (n_dev < 1 || n_dev > n) return fail(MC3D_EINVAL, "n_dev %d out of range [1, %d]", n_dev, n);
+    mc3d_ctx *ctx = new (std::nothrow) mc3d_ctx();
+    if (!ctx) return fail(MC3D_ENOMEM, "out of host memory");
+    ctx->devs.resize(n_dev);
+    std::vector<int> ids(n_dev);
+    for (int k = 0; k < n_dev; ++k) {
+        ids[k] = device_ids ? device_ids[k] : k;
+        if (ids[k] < 0 || ids[k] >= n) { delete ctx; return fail(MC3D_EINVAL, "device id %d out of range", ids[k]); }
+        int rc = init_device(ctx->devs[k], ids[k]);
+        if (rc) { mc3d_destroy(ctx); return rc; }
+    }
+    if (n_dev > 1) {
+        int rc = load_nccl();
+        if (rc) { mc3d_destroy(ctx); return rc; }
+        ctx->comms.assign(n_dev, nullptr);
+        ncclResult_t r = g_nccl.CommInitAll(ctx->comms.data(), n_dev, ids.data());
+        if (r != ncclSuccess) {
+            ctx->comms.clear();
+            mc3d_destroy(ctx);
+            return fail(MC3D_ENCCL, "ncclCommInitAll failed: %s", g_nccl.GetErrorString(r));
+        }
+    }
+    *out = ctx;
+    return MC3D_OK;
+}
+
+int mc3d_nccl_unique_id(uint8_t id_out[128])
+{
+    if (!id_out) return fail(MC3D_EINVAL, "id_out is null");
+    int rc = load_nccl();
+    if (rc) return rc;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    NCCL_TRY(g_nccl.GetUniqueId(&id));
+    memcpy(id_out, &id, 128);
+    return MC3D_OK;
+}
+
+int mc3d_create_rank(mc3d_ctx **out, int device_id, const uint8_t nccl_id[128], int rank, int world_size)
+{
+    if (!out) return fail(MC3D_EINVAL, "ctx out pointer is null");
+    *out = nullptr;
+    if (world_size < 1 || rank < 0 || rank >= world_size) return fail(MC3D_EINVAL, "bad rank %d / world %d", rank, world_size);
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) return fail(MC3D_ENODEVICE, "no CUDA device: %s", cudaGetErrorString(e));
+    if (device_id < 0 || device_id >= n) return fail(MC3D_EINVAL, "device id %d out of range", device_id);
+    mc3d_ctx *ctx = new (std::nothrow) mc3d_ctx();
+    if (!ctx) return fail(MC3D_ENOMEM, "out of host memory");
+    ctx->devs.resize(1);
+    ctx->rank = rank;
+    ctx->world = world_size;
+    int rc = init_device(ctx->devs[0], device_id);
+    if (rc) { mc3d_destroy(ctx); return rc; }
+    if (world_size > 1) {
+        if (!nccl_id) { mc3d_destroy(ctx); return fail(MC3D_EINVAL, "nccl_id is required for world_size > 1"); }
+        rc = load_nccl();
+        if (rc) { mc3d_destroy(ctx); return rc; }
+        ncclUniqueId id;
+        memcpy(&id, nccl_id, 128);
+        ctx->comms.assign(1, nullptr);
+        ncclResult_t r = g_nccl.CommInitRank(&ctx->comms[0], world_size, id, rank);
+        if (r != ncclSuccess) {
+            ctx->comms.clear();
+            mc3d_destroy(ctx);
+            return fail(MC3D_ENCCL, "ncclCommInitRank failed: %s", g_nccl.GetErrorString(r));
+        }
+    }
+    *out = ctx;
+    return MC3D_OK;
+}
+
+int mc3d_destroy(mc3d_ctx *ctx)
+{
+    if (!ctx) return MC3D_OK;
+    for (size_t k = 0; k < ctx->comms.size(); ++k)
+        if (ctx->comms[k] && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comms[k]);
+    for (Device &d : ctx->devs) {
+        if (cudaSetDevice(d.id) != cudaSuccess) continue;
+        if (d.stream) cudaStreamSynchronize(d.stream);
+        for (Slot &s : d.slot) {
+            s.rows.release(); s.edges.release(); s.counters.release(); s.raw.release(); s.condition.release();
+            s.wvl_row.release(); s.theta_n.release(); s.phi_n.release(); s.path_length.release();
+            s.n_scat.release(); s.tally.release();
+            if (s.host_tally) cudaFreeHost(s.host_tally);
+            if (s.host_rows) cudaFreeHost(s.host_rows);
+            if (s.host_edges) cudaFreeHost(s.host_edges);
+            for (cudaEvent_t e : s.ev) cudaEventDestroy(e);
+        }
+        if (d.stream) cudaStreamDestroy(d.stream);
+    }
+    delete ctx;
+    return MC3D_OK;
+}
+
+int mc3d_host_alloc(void **ptr, uint64_t bytes)
+{
+    if (!ptr) return fail(MC3D_EINVAL, "ptr is null");
+    *ptr = nullptr;
+    cudaError_t e = cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocPortable);
+    if (e != cudaSuccess) return fail(MC3D_ENOMEM, "cudaHostAlloc(%llu) failed: %s", (unsigned long long)bytes, cudaGetErrorString(e));
+    return MC3D_OK;
+}
+
+int mc3d_host_free(void *ptr)
+{
+    if (ptr) CUDA_TRY(cudaFreeHost(ptr));
+    return MC3D_OK;
+}
+
+int mc3d_set_launch(mc3d_ctx *ctx, int blocks_per_sm, int block_threads, int refill_threshold)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (block_threads != 0 && block_threads != 128 && block_threads != 256 && block_threads != 512)
+        return fail(MC3D_EINVAL, "block_threads must be 128, 256 or 512");
+    if (blocks_per_sm < 0 || blocks_per_sm > 16) return fail(MC3D_EINVAL, "blocks_per_sm out of range");
+    if (refill_threshold < 0 || refill_threshold > 32) return fail(MC3D_EINVAL, "refill_threshold must be in [1, 32]");
+    if (blocks_per_sm) ctx->blocks_per_sm = blocks_per_sm;
+    if (block_threads) ctx->block_threads = block_threads;
+    if (refill_threshold) ctx->refill_threshold = refill_threshold;
+    return MC3D_OK;
+}
+
+static int validate_run(const mc3d_params *P, const mc3d_ssp_row *table, int n_rows)
+{
+    if (!P || !table) return fail(MC3D_EINVAL, "params / table is null");
+    if (n_rows < 1 || n_rows > 4096) return fail(MC3D_EINVAL, "n_rows %d out of range [1, 4096]", n_rows);
+    if (P->n_theta_bins < 0 || P->n_theta_bins > 65536) return fail(MC3D_EINVAL, "n_theta_bins out of range");
+    if (!(P->tau_tot > 0.0)) return fail(MC3D_EINVAL, "tau_tot must be positive");
+    if (!(P->rho_snw > 0.0)) return fail(MC3D_EINVAL, "rho_snw must be positive");
+    if (!(P->theta0_rad >= 0.0 && P->theta0_rad < 1.5707963267948966))
+        return fail(MC3D_EINVAL, "theta0 must be in [0, pi/2)");
+    if (!(P->sigma_um >= 0.0)) return fail(MC3D_EINVAL, "sigma must be >= 0");
+    if (P->flags & MC3D_FLAG_LAMBERT_SURFACE)
+        return fail(MC3D_EINVAL, "Lambertian_surface mode is not implemented in production mode (use replay)");
+    for (int r = 0; r < n_rows; ++r) {
+        if (!(table[r].ext_cff_mss > 0.0)) return fail(MC3D_EINVAL, "row %d: ext_cff_mss must be positive", r);
+        if (!(table[r].g > -1.0 && table[r].g < 1.0)) return fail(MC3D_EINVAL, "row %d: g must be in (-1, 1)", r);
+    }
+    return MC3D_OK;
+}
+
+int mc3d_run_async(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, const mc3d_ssp_row *table, int n_rows,
+                   uint64_t seed, uint64_t photon_begin, uint64_t n_photon, const mc3d_records *rec,
+                   uint64_t *tally, mc3d_stats *stats)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (slot_idx < 0 || slot_idx >= N_SLOTS) return fail(MC3D_EINVAL, "slot must be 0 or 1");
+    rc = validate_run(P, table, n_rows);
+    if (rc) return rc;
+    for (Device &d : ctx->devs)
+        if (d.slot[slot_idx].busy) return fail(MC3D_EINVAL, "slot %d is busy; call mc3d_wait first", slot_idx);
+    (void)stats;
+    ctx->t0[slot_idx] = std::chrono::steady_clock::now();
+
+    const int n_dev = (int)ctx->devs.size();
+    const int stride = N_COND + P->n_theta_bins;
+    const size_t tally_len = (size_t)n_rows * stride;
+
+    WalkParams W;
+    memset(&W, 0, sizeof W);
+    philox_round_keys(seed, W.rk);
+    W.mu0x = (float)std::sin(P->theta0_rad);
+    W.mu0z = (float)(-std::cos(P->theta0_rad));
+    W.tau_tot = (float)P->tau_tot;
+    W.neg_tau_tot = -W.tau_tot;
+    W.wvl0_x100 = P->wvl0_um * 100.0;
+    W.sigma_x100 = P->sigma_um * 100.0;
+    W.k_first = P->k_first;
+    W.n_rows = n_rows;
+    {
+        const double t = std::floor(std::ldexp(P->r_lambert, 32) - 0.5);
+        W.refl_thr = t < -1.0 ? -1 : (t > 4294967295.0 ? 4294967295ll : (long long)t);
+    }
+    W.lambert_bottom = (P->flags & MC3D_FLAG_LAMBERT_BOTTOM) ? 1u : 0u;
+    W.refill_threshold = (uint32_t)ctx->refill_threshold;
+
+    mc3d_stats &st = ctx->pending_stats[slot_idx];
+    memset(&st, 0, sizeof st);
+    st.n_devices = n_dev;
+    st.sm_count = ctx->devs[0].sm_count;
+    st.sm_clock_khz = ctx->devs[0].clock_khz;
+    st.block_threads = ctx->block_threads;
+    st.n_photon = n_photon;
+
+    for (int k = 0; k < n_dev; ++k) {
+        Device &d = ctx->devs[k];
+        Slot &s = d.slot[slot_idx];
+        uint64_t off, cnt;
+        array_split(n_photon, n_dev, k, &off, &cnt);
+        CUDA_TRY(cudaSetDevice(d.id));
+        const int n_chunks = (int)((cnt + CHUNK_PHOTONS - 1) / CHUNK_PHOTONS);
+        const uint64_t chunk_cap = std::min<uint64_t>(cnt, CHUNK_PHOTONS);
+
+        // ---- buffers
+        CUDA_TRY(s.rows.ensure(n_rows));
+        CUDA_TRY(s.edges.ensure(P->n_theta_bins + 1));
+        CUDA_TRY(s.counters.ensure(std::max(n_chunks, 1)));
+        CUDA_TRY(s.raw.ensure(std::max<uint64_t>(chunk_cap, 1)));
+        CUDA_TRY(s.tally.ensure(tally_len + 1));
+        if (s.host_tally_cap < tally_len + 1) {
+            if (s.host_tally) cudaFreeHost(s.host_tally);
+            s.host_tally = nullptr;
+            CUDA_TRY(cudaHostAlloc((void **)&s.host_tally, (tally_len + 1) * sizeof(unsigned long long), cudaHostAllocPortable));
+            s.host_tally_cap = tally_len + 1;
+        }
+        if (s.host_rows_cap < (size_t)n_rows) {
+            if (s.host_rows) cudaFreeHost(s.host_rows);
+            s.host_rows = nullptr;
+            CUDA_TRY(cudaHostAlloc((void **)&s.host_rows, n_rows * sizeof(DevRow), cudaHostAllocPortable));
+            s.host_rows_cap = n_rows;
+        }
+        if (s.host_edges_cap < (size_t)P->n_theta_bins + 1) {
+            if (s.host_edges) cudaFreeHost(s.host_edges);
+            s.host_edges = nullptr;
+            CUDA_TRY(cudaHostAlloc((void **)&s.host_edges, (P->n_theta_bins + 1) * sizeof(double), cudaHostAllocPortable));
+            s.host_edges_cap = P->n_theta_bins + 1;
+        }
+        const bool want_rec = rec != nullptr;
+        if (want_rec && cnt) {
+            if (rec->condition) CUDA_TRY(s.condition.ensure(chunk_cap));
+            if (rec->wvl_row) CUDA_TRY(s.wvl_row.ensure(chunk_cap));
+            if (rec->theta_n) CUDA_TRY(s.theta_n.ensure(chunk_cap));
+            if (rec->phi_n) CUDA_TRY(s.phi_n.ensure(chunk_cap));
+            if (rec->n_scat) CUDA_TRY(s.n_scat.ensure(chunk_cap));
+            if (rec->path_length) CUDA_TRY(s.path_length.ensure(chunk_cap));
+        }
+        while ((int)s.ev.size() < 2 * std::max(n_chunks, 1)) {
+            cudaEvent_t e;
+            CUDA_TRY(cudaEventCreate(&e));
+            s.ev.push_back(e);
+        }
+
+        // ---- uploads
+        const bool impurity = build_rows(P, table, n_rows, s.host_rows);
+        // np.linspace(0, pi/2, n + 1): start + arange * step with the endpoint forced (numpy/_core/function_base.py)
+        if (P->n_theta_bins > 0) {
+            const double stop = 1.5707963267948966, step = stop / P->n_theta_bins;
+            for (int b = 0; b <= P->n_theta_bins; ++b) s.host_edges[b] = b * step;
+            s.host_edges[P->n_theta_bins] = stop;
+        } else {
+            s.host_edges[0] = 0.0;
+        }
+        CUDA_TRY(cudaMemcpyAsync(s.rows.p, s.host_rows, n_rows * sizeof(DevRow), cudaMemcpyHostToDevice, d.stream));
+        CUDA_TRY(cudaMemcpyAsync(s.edges.p, s.host_edges, (P->n_theta_bins + 1) * sizeof(double), cudaMemcpyHostToDevice, d.stream));
+        CUDA_TRY(cudaMemsetAsync(s.counters.p, 0, std::max(n_chunks, 1) * sizeof(uint32_t), d.stream));
+        CUDA_TRY(cudaMemsetAsync(s.tally.p, 0, (tally_len + 1) * sizeof(unsigned long long), d.stream));
+
+        // ---- launch configuration: persistent grid, SM count x resident blocks
+        int resident = walk_occupancy(impurity, ctx->block_threads, ctx->blocks_per_sm, n_rows);
+        if (resident < 1) return fail(MC3D_ECUDA, "walk kernel does not fit on an SM (block %d, rows %d)", ctx->block_threads, n_rows);
+        resident = std::min(resident, ctx->blocks_per_sm);
+        st.grid_blocks = d.sm_count * resident;
+
+        for (int c = 0; c < n_chunks; ++c) {
+            const uint64_t c_off = (uint64_t)c * CHUNK_PHOTONS;
+            const uint32_t c_cnt = (uint32_t)std::min<uint64_t>(CHUNK_PHOTONS, cnt - c_off);
+            WalkParams Wc = W;
+            Wc.photon_begin = photon_begin + off + c_off;
+            Wc.n_photon = c_cnt;
+            Wc.rows = s.rows.p;
+            Wc.counter = s.counters.p + c;
+            Wc.raw = s.raw.p;
+            const int want = (int)((c_cnt + ctx->block_threads - 1) / ctx->block_threads);
+            const int grid = std::max(1, std::min(st.grid_blocks, want));
+            CUDA_TRY(cudaEventRecord(s.ev[2 * c], d.stream));
+            CUDA_TRY(launch_walk(Wc, impurity, ctx->block_threads, ctx->blocks_per_sm, grid, d.stream));
+            FinalizeParams F;
+            memset(&F, 0, sizeof F);
+            F.raw = s.raw.p;
+            F.rows = s.rows.p;
+            F.edges = s.edges.p;
+            F.n_photon = c_cnt;
+            F.n_rows = n_rows;
+            F.n_theta_bins = P->n_theta_bins;
+            if (want_rec) {
+                F.condition = rec->condition ? s.condition.p : nullptr;
+                F.wvl_row = rec->wvl_row ? s.wvl_row.p : nullptr;
+                F.theta_n = rec->theta_n ? s.theta_n.p : nullptr;
+                F.phi_n = rec->phi_n ? s.phi_n.p : nullptr;
+                F.n_scat = rec->n_scat ? s.n_scat.p : nullptr;
+                F.path_length = rec->path_length ? s.path_length.p : nullptr;
+            }
+            F.tally = s.tally.p;
+            F.n_events = s.tally.p + tally_len;
+            CUDA_TRY(launch_finalize(F, d.sm_count, d.stream));
+            CUDA_TRY(cudaEventRecord(s.ev[2 * c + 1], d.stream));
+            if (want_rec) {
+                const uint64_t o = off + c_off;
+#define COPY_COL(col, T)                                                                                       \
+    if (rec->col)                                                                                              \
+        CUDA_TRY(cudaMemcpyAsync(rec->col + o, s.col.p, (size_t)c_cnt * sizeof(T), cudaMemcpyDeviceToHost, d.stream))
+                COPY_COL(condition, uint8_t);
+                COPY_COL(wvl_row, int16_t);
+                COPY_COL(theta_n, float);
+                COPY_COL(phi_n, float);
+                COPY_COL(n_scat, uint32_t);
+                COPY_COL(path_length, float);
+#undef COPY_COL
+            }
+        }
+        s.busy = true;
+        s.n_photon = cnt;
+        s.tally_len = tally_len;
+        s.n_chunks = n_chunks;
+        s.user_tally = tally;
+    }
+
+    // ---- the only collective: sum the tally blocks of all devices of this process onto device 0 (NVLink)
+    if (n_dev > 1) {
+        NCCL_TRY(g_nccl.GroupStart());
+        for (int k = 0; k < n_dev; ++k) {
+            Device &d = ctx->devs[k];
+            Slot &s = d.slot[slot_idx];
+            NCCL_TRY(g_nccl.Reduce(s.tally.p, s.tally.p, tally_len + 1, ncclUint64, ncclSum, 0, ctx->comms[k], d.stream));
+        }
+        NCCL_TRY(g_nccl.GroupEnd());
+    }
+    {
+        Device &d = ctx->devs[0];
+        Slot &s = d.slot[slot_idx];
+        CUDA_TRY(cudaSetDevice(d.id));
+        CUDA_TRY(cudaMemcpyAsync(s.host_tally, s.tally.p, (tally_len + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, d.stream));
+    }
+    return MC3D_OK;
+}
+
+int mc3d_wait(mc3d_ctx *ctx, int slot_idx, mc3d_stats *stats)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (slot_idx < 0 || slot_idx >= N_SLOTS) return fail(MC3D_EINVAL, "slot must be 0 or 1");
+    if (!ctx->devs[0].slot[slot_idx].busy) return fail(MC3D_EINVAL, "slot %d has no call in flight", slot_idx);
+    mc3d_stats &st = ctx->pending_stats[slot_idx];
+    double kernel_ms = 0.0;
+    int first_err = MC3D_OK;
+    for (Device &d : ctx->devs) {
+        Slot &s = d.slot[slot_idx];
+        cudaSetDevice(d.id);
+        cudaError_t e = cudaStreamSynchronize(d.stream);
+        s.busy = false;
+        if (e != cudaSuccess) {
+            if (!first_err) first_err = fail(MC3D_ECUDA, "device %d: %s", d.id, cudaGetErrorString(e));
+            continue;
+        }
+        double ms = 0.0;
+        for (int c = 0; c < s.n_chunks; ++c) {
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, s.ev[2 * c], s.ev[2 * c + 1]) == cudaSuccess) ms += t;
+        }
+        kernel_ms = std::max(kernel_ms, ms);
+    }
+    if (first_err) return first_err;
+    Slot &s0 = ctx->devs[0].slot[slot_idx];
+    st.n_events = s0.host_tally[s0.tally_len];
+    if (s0.user_tally) memcpy(s0.user_tally, s0.host_tally, s0.tally_len * sizeof(uint64_t));
+    st.kernel_ms = kernel_ms;
+    st.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - ctx->t0[slot_idx]).count();
+    if (stats) *stats = st;
+    return MC3D_OK;
+}
+
+int mc3d_run(mc3d_ctx *ctx, const mc3d_params *params, const mc3d_ssp_row *table, int n_rows, uint64_t seed,
+             uint64_t photon_begin, uint64_t n_photon, const mc3d_records *records, uint64_t *tally,
+             mc3d_stats *stats)
+{
+    int rc = mc3d_run_async(ctx, 0, params, table, n_rows, seed, photon_begin, n_photon, records, tally, stats);
+    if (rc) {
+        if (ctx) for (Device &d : ctx->devs) { cudaSetDevice(d.id); cudaStreamSynchronize(d.stream); d.slot[0].busy = false; }
+        return rc;
+    }
+    return mc3d_wait(ctx, 0, stats);
+}
+
+int mc3d_reduce_tally(mc3d_ctx *ctx, uint64_t *tally, uint64_t n, int root)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (!tally && n) return fail(MC3D_EINVAL, "tally is null");
+    if (ctx->world == 1) return MC3D_OK;
+    if (root < 0 || root >= ctx->world) return fail(MC3D_EINVAL, "root %d out of range", root);
+    Device &d = ctx->devs[0];
+    CUDA_TRY(cudaSetDevice(d.id));
+    unsigned long long *buf = nullptr;
+    CUDA_TRY(cudaMalloc((void **)&buf, std::max<uint64_t>(n, 1) * sizeof(unsigned long long)));
+    cudaError_t e = cudaMemcpyAsync(buf, tally, n * sizeof(uint64_t), cudaMemcpyHostToDevice, d.stream);
+    ncclResult_t r = ncclSuccess;
+    if (e == cudaSuccess) r = g_nccl.Reduce(buf, buf, n, ncclUint64, ncclSum, root, ctx->comms[0], d.stream);
+    if (e == cudaSuccess && r == ncclSuccess && ctx->rank == root)
+        e = cudaMemcpyAsync(tally, buf, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, d.stream);
+    cudaError_t e2 = cudaStreamSynchronize(d.stream);
+    cudaFree(buf);
+    if (r != ncclSuccess) return fail(MC3D_ENCCL, "ncclReduce failed: %s", g_nccl.GetErrorString(r));
+    if (e != cudaSuccess) return fail(MC3D_ECUDA, "tally copy failed: %s", cudaGetErrorString(e));
+    if (e2 != cudaSuccess) return fail(MC3D_ECUDA, "stream sync failed: %s", cudaGetErrorString(e2));
+    return MC3D_OK;
+}
+
+int mc3d_replay(mc3d_ctx *ctx, const mc3d_params *P, uint64_t n, const double *wvl, const double *ssa_ice,
+                const double *ssa_imp, const double *g, const double *ext_cff_mss, const double *p_ext_imp,
+                const double *init_draws, const int64_t *offsets, const double *stream, const mc3d_records_f64 *out,
+                uint64_t *n_mismatch)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (!P || !wvl || !ssa_ice || !ssa_imp || !g || !ext_cff_mss || !p_ext_imp || !init_draws || !offsets || !out)
+        return fail(MC3D_EINVAL, "null argument");
+    if (n_mismatch) *n_mismatch = 0;
+    if (n == 0) return MC3D_OK;
+    if (n >= (1ull << 31)) return fail(MC3D_EINVAL, "replay supports < 2^31 photons per call");
+    if (offsets[0] != 0) return fail(MC3D_ESTREAM, "offsets[0] must be 0");
+    for (uint64_t p = 0; p < n; ++p)
+        if (offsets[p + 1] < offsets[p]) return fail(MC3D_ESTREAM, "offsets must be non-decreasing (photon %llu)", (unsigned long long)p);
+    const uint64_t n_stream = (uint64_t)offsets[n];
+    if (n_stream && !stream) return fail(MC3D_EINVAL, "stream is null");
+    Device &d = ctx->devs[0];
+    CUDA_TRY(cudaSetDevice(d.id));
+
+    // one arena: 6 + 3 per-photon double inputs, offsets, stream, then outputs
+    const size_t n_in = 9 * n, n_outd = 5 * n;
+    double *d_in = nullptr, *d_stream = nullptr, *d_outd = nullptr;
+    long long *d_off = nullptr, *d_outl = nullptr;
+    int *d_cond = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(d_in); cudaFree(d_stream); cudaFree(d_outd); cudaFree(d_off); cudaFree(d_outl); cudaFree(d_cond);
+    };
+#define TRY_OR_CLEAN(expr)                                                                       \
+    do {                                                                                           \
+        cudaError_t e_ = (expr);                                                                   \
+        if (e_ != cudaSuccess) { cleanup(); return fail(MC3D_ECUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); } \
+    } while (0)
+    TRY_OR_CLEAN(cudaMalloc((void **)&d_in, n_in * sizeof(double)));
+    TRY_OR_CLEAN(cudaMalloc((void **)&d_stream, std::max<uint64_t>(n_stream, 1) * sizeof(double)));
+    TRY_OR_CLEAN(cudaMalloc((void **)&d_outd, n_outd * sizeof(double)));
+    TRY_OR_CLEAN(cudaMalloc((void **)&d_off, (n + 1) * sizeof(long long)));
+    TRY_OR_CLEAN(cudaMalloc((void **)&d_outl, 2 * n * sizeof(long long)));
+    TRY_OR_CLEAN(cudaMalloc((void **)&d_cond, n * sizeof(int)));
+    const double *ins[6] = {wvl, ssa_ice, ssa_imp, g, ext_cff_mss, p_ext_imp};
+    for (int k = 0; k < 6; ++k)
+        TRY_OR_CLEAN(cudaMemcpyAsync(d_in + k * n, ins[k], n * sizeof(double), cudaMemcpyHostToDevice, d.stream));
+    TRY_OR_CLEAN(cudaMemcpyAsync(d_in + 6 * n, init_draws, 3 * n * sizeof(double), cudaMemcpyHostToDevice, d.stream));
+    TRY_OR_CLEAN(cudaMemcpyAsync(d_off, offsets, (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, d.stream));
+    if (n_stream)
+        TRY_OR_CLEAN(cudaMemcpyAsync(d_stream, stream, n_stream * sizeof(double), cudaMemcpyHostToDevice, d.stream));
+
+    ReplayParams R;
+    memset(&R, 0, sizeof R);
+    R.theta0_rad = P->theta0_rad; R.tau_tot = P->tau_tot; R.rho_snw = P->rho_snw; R.r_lambert = P->r_lambert;
+    R.flags = P->flags;
+    R.n_photon = (uint32_t)n;
+    R.wvl = d_in; R.ssa_ice = d_in + n; R.ssa_imp = d_in + 2 * n; R.g = d_in + 3 * n; R.ext_cff_mss = d_in + 4 * n;
+    R.p_ext_imp = d_in + 5 * n; R.init_draws = d_in + 6 * n;
+    R.offsets = d_off; R.stream = d_stream;
+    R.condition = d_cond;
+    R.wvn = d_outd; R.theta_n = d_outd + n; R.phi_n = d_outd + 2 * n; R.path_length = d_outd + 3 * n;
+    R.snow_depth = d_outd + 4 * n;
+    R.n_scat = d_outl; R.consumed = d_outl + n;
+    TRY_OR_CLEAN(launch_replay(R, d.stream));
+
+    std::vector<long long> consumed(n);
+#define BACK(dst, src, T) \
+    if (dst) TRY_OR_CLEAN(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyDeviceToHost, d.stream))
+    BACK(out->condition, d_cond, int);
+    BACK(out->wvn, R.wvn, double);
+    BACK(out->theta_n, R.theta_n, double);
+    BACK(out->phi_n, R.phi_n, double);
+    BACK(out->path_length, R.path_length, double);
+    BACK(out->snow_depth, R.snow_depth, double);
+    BACK(out->n_scat, R.n_scat, long long);
+    BACK(consumed.data(), R.consumed, long long);
+#undef BACK
+    TRY_OR_CLEAN(cudaStreamSynchronize(d.stream));
+#undef TRY_OR_CLEAN
+    cleanup();
+    uint64_t mism = 0;
+    for (uint64_t p = 0; p < n; ++p) {
+        if (out->consumed) out->consumed[p] = consumed[p];
+        if (consumed[p] != offsets[p + 1] - offsets[p]) ++mism;
+    }
+    if (n_mismatch) *n_mismatch = mism;
+    return MC3D_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,128 @@
+// mc3d_device.cuh -- types shared by the walk / finalize / replay kernels and the host runtime.
+//
+// Random-number layout (identical in oracle/mc3d_oracle.c, which is how production mode is checked):
+//   Philox4x32-10, key = (seed_lo, seed_hi), counter = (c0, c1, pid_lo, pid_hi), pid = global photon id.
+//   c1 low byte is the stream tag:
+//     TAG_EVENT      c0 = event number i (1-based).  w0 -> r1 of Henyey_Greenstein2 (reference
+//                    monte_carlo3D.py:915-916), w1>>8 -> azimuth (921), w2 -> free path (1014),
+//                    (w3<<8 | w1&0xff) -> 40-bit single-scatter-albedo variate (1020)
+//     TAG_SPECIES    c0 = i>>2, word i&3 -> ice/impurity choice (1023); drawn only when an impurity is present
+//     TAG_LAMBERT    c0 = i; sub-block 0 word 0 -> bottom reflectance draw (1422/1453); sub-block 1+(j>>1),
+//                    words 2(j&1), 2(j&1)+1 -> attempt j of the cosine-law rejection loop (1245-1246)
+//     TAG_WAVELENGTH c0 = 0; w0, w1 -> Box-Muller normal for the photon's wavelength (1519)
+//   A 32-bit word w maps to the open-interval uniform (w + 0.5) 2^-32.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace mc3d {
+
+constexpr uint32_t TAG_EVENT = 0, TAG_SPECIES = 1, TAG_LAMBERT = 2, TAG_WAVELENGTH = 3;
+constexpr uint32_t PHILOX_M0 = 0xD2511F53u, PHILOX_M1 = 0xCD9E8D57u;
+constexpr uint32_t PHILOX_W0 = 0x9E3779B9u, PHILOX_W1 = 0xBB67AE85u;
+constexpr int N_COND = 8;
+
+// Per-wavelength row in the form the walk consumes (built on the host from mc3d_ssp_row, fp64 -> fp32/integer).
+struct DevRow {
+    float one_m_g;    // 1 - g
+    float one_m_g2;   // 1 - g^2
+    float two_g;      // 2 g
+    uint32_t flip;    // 0xffffffff when g == 0 (maps the factored HG form onto the reference's 1 - 2r branch)
+    uint32_t t_hi;    // ice: absorbed iff K40 >= T40 = ceil(ssa 2^40 - 1/2); t_hi = T40 >> 8 (saturated)
+    uint32_t t_lo;    //      t_lo = T40 & 0xff, or 256 when T40 == 2^40 (never absorbed)
+    uint32_t ti_hi;   // same for the impurity's single-scatter albedo
+    uint32_t ti_lo;
+    uint32_t s_last;  // impurity iff species word <= s_last (and s_any)
+    uint32_t s_any;   // 0 when P_ext_imp == 0 (species word never selects the impurity)
+    float inv_ext;    // 1 / (ext_cff_mss rho_snw): metres per unit optical depth
+    float pad;
+};
+
+// Raw result of one walk (32 B, one sector, written by the lane that finished the photon).
+struct __align__(16) RawResult {
+    float ux, uy, uz;   // final direction cosines
+    float path_tau;     // path inside the slab in optical-depth units
+    uint32_t n_scat;    // i - 1
+    uint32_t meta;      // condition | row << 8
+    uint32_t pad0, pad1;
+};
+
+struct WalkParams {
+    uint32_t rk[20];        // Philox round keys: rk[2r], rk[2r+1] for round r
+    float mu0x, mu0z;       // sin(theta0), -cos(theta0)
+    float neg_tau_tot;      // -tau_tot
+    float tau_tot;
+    double wvl0_x100, sigma_x100;  // wavelength draw in units of 0.01 um
+    int32_t k_first;
+    int32_t n_rows;
+    int64_t refl_thr;       // bottom reflects iff (int64)w <= refl_thr  (U(w) <= R)
+    uint32_t lambert_bottom;
+    uint32_t refill_threshold;
+    uint64_t photon_begin;  // global id of photon 0 of this launch
+    uint32_t n_photon;      // photons in this launch (< 2^31)
+    uint32_t pad;
+    const DevRow *rows;     // [n_rows], global
+    uint32_t *counter;      // next unclaimed photon offset
+    RawResult *raw;         // [n_photon]
+};
+
+struct FinalizeParams {
+    const RawResult *raw;
+    const DevRow *rows;
+    const double *edges;     // [n_theta_bins + 1] = np.linspace(0, pi/2, n + 1)
+    uint32_t n_photon;
+    int32_t n_rows;
+    int32_t n_theta_bins;
+    int32_t use_smem;
+    // record columns (device), any may be null
+    uint8_t *condition;
+    int16_t *wvl_row;
+    float *theta_n;
+    float *phi_n;
+    uint32_t *n_scat;
+    float *path_length;
+    unsigned long long *tally;   // [n_rows][N_COND + n_theta_bins] or null
+    unsigned long long *n_events;
+};
+
+// fp64 replay mode (replay_kernel.cu): per-photon inputs exactly as the reference holds them
+struct ReplayParams {
+    double theta0_rad, tau_tot, rho_snw, r_lambert;
+    uint32_t flags;
+    uint32_t n_photon;
+    const double *wvl, *ssa_ice, *ssa_imp, *g, *ext_cff_mss, *p_ext_imp;
+    const double *init_draws;      // [3 n]
+    const long long *offsets;      // [n + 1]
+    const double *stream;
+    int *condition;
+    double *wvn, *theta_n, *phi_n, *path_length, *snow_depth;
+    long long *n_scat, *consumed;
+};
+
+__device__ __forceinline__ void philox_round(uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c3, uint32_t k0,
+                                             uint32_t k1)
+{
+    const uint32_t h0 = __umulhi(PHILOX_M0, c0), l0 = PHILOX_M0 * c0;
+    const uint32_t h1 = __umulhi(PHILOX_M1, c2), l1 = PHILOX_M1 * c2;
+    c0 = h1 ^ c1 ^ k0;
+    c1 = l1;
+    c2 = h0 ^ c3 ^ k1;
+    c3 = l0;
+}
+
+// rk: 20 precomputed round keys (kernel parameter space -> constant bank operands of the LOP3s)
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                               const uint32_t *__restrict__ rk)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) philox_round(c0, c1, c2, c3, rk[2 * r], rk[2 * r + 1]);
+    return make_uint4(c0, c1, c2, c3);
+}
+
+__device__ __forceinline__ float u32_to_unit(uint32_t w)
+{
+    // (w + 0.5) 2^-32, never 0; rounds to 1.0f only for w > 0xffffff7f where -log gives exactly 0
+    return fmaf(__uint2float_rn(w), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+}
+
+}  // namespace mc3d

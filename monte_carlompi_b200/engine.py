@@ -1,0 +1,281 @@
+"""ctypes binding of libmc3d.so (include/mc3d.h) -- the only way this package computes anything.
+
+There is no CPU fallback: if the shared library is missing, or no B200 is visible, the constructors raise.
+No PyTorch, no Triton; numpy arrays in, numpy arrays out.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libmc3d.so')
+
+N_COND = 8
+FLAG_LAMBERT_BOTTOM = 1
+FLAG_LAMBERT_SURFACE = 2
+ABI_VERSION = 1
+
+EXPORTS = ('mc3d_abi_version', 'mc3d_last_error', 'mc3d_query', 'mc3d_create', 'mc3d_nccl_unique_id',
+           'mc3d_create_rank', 'mc3d_destroy', 'mc3d_host_alloc', 'mc3d_host_free', 'mc3d_run', 'mc3d_run_async',
+           'mc3d_wait', 'mc3d_reduce_tally', 'mc3d_replay', 'mc3d_set_launch')
+
+
+class Mc3dError(RuntimeError):
+    pass
+
+
+class Params(C.Structure):
+    _fields_ = [('theta0_rad', C.c_double), ('tau_tot', C.c_double), ('rho_snw', C.c_double),
+                ('r_lambert', C.c_double), ('wvl0_um', C.c_double), ('sigma_um', C.c_double),
+                ('k_first', C.c_int32), ('flags', C.c_uint32), ('n_theta_bins', C.c_int32),
+                ('reserved', C.c_int32)]
+
+
+class Records(C.Structure):
+    _fields_ = [('condition', C.c_void_p), ('wvl_row', C.c_void_p), ('theta_n', C.c_void_p),
+                ('phi_n', C.c_void_p), ('n_scat', C.c_void_p), ('path_length', C.c_void_p)]
+
+
+class RecordsF64(C.Structure):
+    _fields_ = [('condition', C.c_void_p), ('wvn', C.c_void_p), ('theta_n', C.c_void_p), ('phi_n', C.c_void_p),
+                ('n_scat', C.c_void_p), ('path_length', C.c_void_p), ('snow_depth', C.c_void_p),
+                ('consumed', C.c_void_p)]
+
+
+class Stats(C.Structure):
+    _fields_ = [('n_photon', C.c_uint64), ('n_events', C.c_uint64), ('kernel_ms', C.c_double),
+                ('total_ms', C.c_double), ('n_devices', C.c_int32), ('sm_count', C.c_int32),
+                ('sm_clock_khz', C.c_int32), ('grid_blocks', C.c_int32), ('block_threads', C.c_int32),
+                ('reserved', C.c_int32)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != 'reserved'}
+
+
+ROW_DTYPE = np.dtype([('wvl_um', 'f8'), ('ssa_ice', 'f8'), ('ssa_imp', 'f8'), ('g', 'f8'),
+                      ('ext_cff_mss', 'f8'), ('p_ext_imp', 'f8')])
+
+RECORD_COLUMNS = (('condition', np.uint8), ('wvl_row', np.int16), ('theta_n', np.float32),
+                  ('phi_n', np.float32), ('n_scat', np.uint32), ('path_length', np.float32))
+
+_lib = None
+
+
+def load_library():
+    """dlopen libmc3d.so and declare the prototypes.  Raises Mc3dError when the library has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise Mc3dError('%s not found: build it with `make -C %s` (or __graft_entry__.build()); there is no '
+                        'CPU fallback' % (LIB_PATH, os.path.join(_HERE, 'csrc')))
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, u64 = C.c_void_p, C.c_int, C.c_uint64
+    lib.mc3d_abi_version.restype = i32
+    lib.mc3d_last_error.restype = C.c_char_p
+    lib.mc3d_query.argtypes = [i32, vp, vp, vp, vp, vp, vp]
+    lib.mc3d_create.argtypes = [vp, vp, i32]
+    lib.mc3d_nccl_unique_id.argtypes = [vp]
+    lib.mc3d_create_rank.argtypes = [vp, i32, vp, i32, i32]
+    lib.mc3d_destroy.argtypes = [vp]
+    lib.mc3d_host_alloc.argtypes = [vp, u64]
+    lib.mc3d_host_free.argtypes = [vp]
+    lib.mc3d_run.argtypes = [vp, vp, vp, i32, u64, u64, u64, vp, vp, vp]
+    lib.mc3d_run_async.argtypes = [vp, i32, vp, vp, i32, u64, u64, u64, vp, vp, vp]
+    lib.mc3d_wait.argtypes = [vp, i32, vp]
+    lib.mc3d_reduce_tally.argtypes = [vp, vp, u64, i32]
+    lib.mc3d_replay.argtypes = [vp, vp, u64] + [vp] * 11
+    lib.mc3d_set_launch.argtypes = [vp, i32, i32, i32]
+    if lib.mc3d_abi_version() != ABI_VERSION:
+        raise Mc3dError('libmc3d.so ABI %d != expected %d' % (lib.mc3d_abi_version(), ABI_VERSION))
+    _lib = lib
+    return lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise Mc3dError('libmc3d error %d: %s' % (rc, load_library().mc3d_last_error().decode('utf-8', 'replace')))
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def query(device=0):
+    """(n_devices, sm_count, sm_clock_khz, global_mem_bytes, cc_major, cc_minor) of a CUDA device."""
+    lib = load_library()
+    n, sm, clk, maj, mnr = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0)
+    mem = C.c_uint64(0)
+    _check(lib.mc3d_query(device, C.byref(n), C.byref(sm), C.byref(clk), C.byref(mem), C.byref(maj), C.byref(mnr)))
+    return dict(n_devices=n.value, sm_count=sm.value, sm_clock_khz=clk.value, global_mem_bytes=mem.value,
+                cc_major=maj.value, cc_minor=mnr.value)
+
+
+def device_count():
+    lib = load_library()
+    n = C.c_int(0)
+    lib.mc3d_query(0, C.byref(n), None, None, None, None, None)
+    return n.value
+
+
+def nccl_unique_id():
+    buf = (C.c_uint8 * 128)()
+    _check(load_library().mc3d_nccl_unique_id(buf))
+    return bytes(buf)
+
+
+def make_params(theta0_rad, tau_tot, rho_snw, r_lambert, wvl0_um, sigma_um, k_first, lambert_bottom=True,
+                lambert_surface=False, n_theta_bins=0):
+    flags = (FLAG_LAMBERT_BOTTOM if lambert_bottom else 0) | (FLAG_LAMBERT_SURFACE if lambert_surface else 0)
+    return Params(float(theta0_rad), float(tau_tot), float(rho_snw), float(r_lambert), float(wvl0_um),
+                  float(sigma_um), int(k_first), flags, int(n_theta_bins), 0)
+
+
+class PinnedArray(object):
+    """numpy view of page-locked host memory from mc3d_host_alloc (so record copy-back runs at PCIe speed)."""
+
+    def __init__(self, shape, dtype):
+        self._lib = load_library()
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) if np.ndim(shape) else int(shape)
+        self._ptr = C.c_void_p(0)
+        _check(self._lib.mc3d_host_alloc(C.byref(self._ptr), max(1, n * dtype.itemsize)))
+        buf = (C.c_uint8 * max(1, n * dtype.itemsize)).from_address(self._ptr.value)
+        self.array = np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
+
+    def free(self):
+        if self._ptr is not None and self._ptr.value:
+            self.array = None
+            self._lib.mc3d_host_free(self._ptr)
+            self._ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class RecordBuffers(object):
+    """One set of pinned SoA record columns for up to ``capacity`` photons."""
+
+    def __init__(self, capacity):
+        self.capacity = int(capacity)
+        self._pinned = {name: PinnedArray(self.capacity, dt) for name, dt in RECORD_COLUMNS}
+        self.struct = Records(*[self._pinned[name].array.ctypes.data for name, _ in RECORD_COLUMNS])
+
+    def view(self, n):
+        return {name: self._pinned[name].array[:n] for name, _ in RECORD_COLUMNS}
+
+    def free(self):
+        for p in self._pinned.values():
+            p.free()
+
+
+class Context(object):
+    """A libmc3d context: either one process driving ``devices`` (list of CUDA ordinals), or rank ``rank`` of
+    ``world_size`` single-GPU processes sharing ``nccl_id`` (torchrun / mpirun style)."""
+
+    def __init__(self, devices=None, rank=None, world_size=None, nccl_id=None, device=None):
+        self._lib = load_library()
+        self._ctx = C.c_void_p(0)
+        if rank is None:
+            if devices is None:
+                devices = [0]
+            ids = (C.c_int * len(devices))(*devices)
+            _check(self._lib.mc3d_create(C.byref(self._ctx), ids, len(devices)))
+            self.rank, self.world_size, self.n_devices = 0, 1, len(devices)
+        else:
+            idbuf = None
+            if world_size > 1:
+                idbuf = (C.c_uint8 * 128).from_buffer_copy(nccl_id)
+            _check(self._lib.mc3d_create_rank(C.byref(self._ctx), int(device if device is not None else 0), idbuf,
+                                              int(rank), int(world_size)))
+            self.rank, self.world_size, self.n_devices = int(rank), int(world_size), 1
+        self._keep = [None, None]
+
+    def close(self):
+        if self._ctx is not None and self._ctx.value:
+            self._lib.mc3d_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def set_launch(self, blocks_per_sm=0, block_threads=0, refill_threshold=0):
+        _check(self._lib.mc3d_set_launch(self._ctx, blocks_per_sm, block_threads, refill_threshold))
+
+    # ---- production mode ------------------------------------------------------------------------------------
+    def run_async(self, slot, params, table, seed, photon_begin, n_photon, records=None, tally=None):
+        """Enqueue one walk.  ``records``: RecordBuffers, dict of numpy columns, or None.  ``tally``: uint64 array
+        of shape (n_rows, N_COND + n_theta_bins) or None.  Buffers must stay alive until ``wait(slot)``."""
+        table = np.ascontiguousarray(table, dtype=ROW_DTYPE)
+        rec_struct = None
+        if isinstance(records, RecordBuffers):
+            rec_struct = records.struct
+        elif records is not None:
+            rec_struct = Records(*[records[name].ctypes.data if records.get(name) is not None else None
+                                   for name, _ in RECORD_COLUMNS])
+        if tally is not None:
+            assert tally.dtype == np.uint64 and tally.flags.c_contiguous
+            assert tally.size == len(table) * (N_COND + params.n_theta_bins)
+        self._keep[slot] = (params, table, rec_struct, records, tally)
+        _check(self._lib.mc3d_run_async(self._ctx, slot, C.byref(params), _ptr(table), len(table), int(seed),
+                                        int(photon_begin), int(n_photon),
+                                        C.byref(rec_struct) if rec_struct is not None else None, _ptr(tally), None))
+
+    def wait(self, slot):
+        st = Stats()
+        _check(self._lib.mc3d_wait(self._ctx, slot, C.byref(st)))
+        self._keep[slot] = None
+        return st.as_dict()
+
+    def run(self, params, table, seed, photon_begin, n_photon, records=True, tally=True):
+        """Synchronous walk of photon ids [photon_begin, photon_begin + n_photon).
+        Returns (records dict or None, tally array or None, stats dict)."""
+        table = np.ascontiguousarray(table, dtype=ROW_DTYPE)
+        rec = None
+        if records:
+            rec = {name: np.empty(n_photon, dtype=dt) for name, dt in RECORD_COLUMNS}
+        t = np.zeros((len(table), N_COND + params.n_theta_bins), np.uint64) if tally else None
+        self.run_async(0, params, table, seed, photon_begin, n_photon, rec, t)
+        stats = self.wait(0)
+        return rec, t, stats
+
+    def reduce_tally(self, tally, root=0):
+        """Sum a uint64 tally over the ranks of a multi-rank context (one ncclReduce); in place on ``root``."""
+        assert tally.dtype == np.uint64 and tally.flags.c_contiguous
+        _check(self._lib.mc3d_reduce_tally(self._ctx, _ptr(tally), tally.size, int(root)))
+        return tally
+
+    # ---- replay mode ----------------------------------------------------------------------------------------
+    def replay(self, params, wvl, ssa_ice, ssa_imp, g, ext_cff_mss, p_ext_imp, init_draws, offsets, stream):
+        """fp64 walk over the reference's recorded random stream (see mc3d_replay in include/mc3d.h)."""
+        f8 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        wvl, ssa_ice, ssa_imp, g, ext_cff_mss, p_ext_imp = map(f8, (wvl, ssa_ice, ssa_imp, g, ext_cff_mss,
+                                                                     p_ext_imp))
+        init_draws, stream = f8(init_draws), f8(stream)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = len(wvl)
+        assert len(init_draws) == 3 * n and len(offsets) == n + 1 and len(stream) >= offsets[-1]
+        out = {'condition': np.zeros(n, np.int32), 'wvn': np.zeros(n), 'theta_n': np.zeros(n),
+               'phi_n': np.zeros(n), 'n_scat': np.zeros(n, np.int64), 'path_length': np.zeros(n),
+               'snow_depth': np.zeros(n), 'consumed': np.zeros(n, np.int64)}
+        rec = RecordsF64(*[out[k].ctypes.data for k in ('condition', 'wvn', 'theta_n', 'phi_n', 'n_scat',
+                                                        'path_length', 'snow_depth', 'consumed')])
+        mism = C.c_uint64(0)
+        _check(self._lib.mc3d_replay(self._ctx, C.byref(params), n, _ptr(wvl), _ptr(ssa_ice), _ptr(ssa_imp), _ptr(g),
+                                     _ptr(ext_cff_mss), _ptr(p_ext_imp), _ptr(init_draws), _ptr(offsets),
+                                     _ptr(stream), C.byref(rec), C.byref(mism)))
+        out['n_mismatch'] = int(mism.value)
+        return out

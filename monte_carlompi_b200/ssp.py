@@ -1,0 +1,120 @@
+"""Per-wavelength single-scattering properties (SSP) for the walk: host-side input preparation.
+
+Restates, per *distinct* rounded wavelength instead of per photon, what the reference does at
+monte_carloMPI/monte_carlo3D.py:498-658 (get_optical_properties), 661-777 (get_impurity_optics) and 1575-1588, 1612
+(extinction mix, impurity probability, snow depth).  The result is the table uploaded to the GPU
+(``mc3d_ssp_row`` in include/mc3d.h): row r holds wavelength (k_first + r) / 100 um.
+
+Lookup rule of the reference, reproduced exactly (same IEEE operations as scipy's interp1d on two points):
+  * the two table rows nearest to the wavelength are selected (argsort of |wvl - wvl_in|, :2);
+  * if the wavelength lies inside their bracket: linear interpolation
+        y = ((y_hi - y_lo) / (x_hi - x_lo)) * (x - x_lo) + y_lo
+  * otherwise interp1d raises ValueError and the reference falls back to the nearest row's value, printing
+    'error: exception raised while interpolating <name>, using nearest value instead' on stderr.
+"""
+import os
+import sys
+
+import numpy as np
+from scipy.io import netcdf_file
+
+from .engine import ROW_DTYPE
+
+
+def read_table(path, names):
+    """Read 1-D variables ``names`` from a NetCDF-3 file (monte_carlo3D.py:509-514, 667-671)."""
+    f = netcdf_file(path, 'r', mmap=False)
+    try:
+        return {n: np.array(f.variables[n].data) for n in names}
+    finally:
+        f.close()
+
+
+def nearest_pair_interp(wvl_in, columns, wvls_um, warn_names=None):
+    """Evaluate ``columns`` (dict name -> array over the table) at each wavelength of ``wvls_um`` [um].
+
+    ``wvl_in`` is the table's wavelength axis in metres.  Returns dict name -> float64 array."""
+    wvls_um = np.atleast_1d(np.asarray(wvls_um, dtype=np.float64))
+    out = {n: np.empty(wvls_um.shape, dtype=np.float64) for n in columns}
+    for j, w_um in enumerate(wvls_um):
+        wvl = w_um * 1e-6                                           # monte_carlo3D.py:519, 594
+        idx = np.argsort(np.absolute(wvl - wvl_in))[:2]             # monte_carlo3D.py:522, 596
+        x = wvl_in[idx]
+        if not x[0] < x[1]:                                         # monte_carlo3D.py:528-535
+            idx = idx[::-1]
+            x = x[::-1]
+        inside = bool(x[0] <= wvl <= x[1]) and bool(x[0] < x[1])    # interp1d(bounds_error=True)
+        for n, col in columns.items():
+            y = col[idx]
+            if inside:
+                slope = (y[1] - y[0]) / (x[1] - x[0])
+                out[n][j] = slope * (wvl - x[0]) + y[0]
+            else:
+                # ValueError path: value of the nearest row (idx_wvl[0] in the reference's ordering)
+                nearest = np.argsort(np.absolute(wvl - wvl_in))[0]
+                out[n][j] = col[nearest]
+                if warn_names is not None:
+                    sys.stderr.write('error: exception raised while interpolating %s, using nearest value '
+                                     'instead\n' % warn_names.get(n, n))
+    return out
+
+
+def ice_file(optics_dir, rds_snw):
+    return os.path.join(optics_dir, 'mie', 'snicar', 'ice_wrn_%04d.nc' % rds_snw)   # monte_carlo3D.py:507-508
+
+
+def impurity_file(optics_dir, fi_imp):
+    return os.path.join(optics_dir, 'mie', 'snicar', fi_imp)                        # monte_carlo3D.py:666
+
+
+def wavelength_grid(wvl0, sigma, n_sigma=7.0):
+    """Integer grid k (wavelength = k / 100 um) covering wvl0 +- n_sigma sigma.
+
+    The device draws Box-Muller normals from 32-bit uniforms, |z| <= sqrt(-2 ln 2^-33) = 6.76, so 7 sigma covers
+    every wavelength np.around(normal(wvl0, sigma), 2) (monte_carlo3D.py:1519-1520) can produce here."""
+    k_lo = int(np.floor((wvl0 - n_sigma * sigma) * 100.0)) - 1
+    k_hi = int(np.ceil((wvl0 + n_sigma * sigma) * 100.0)) + 1
+    k_lo = max(k_lo, 1)
+    k_hi = max(k_hi, k_lo)
+    return k_lo, k_hi
+
+
+def build_table(optics_dir, fi_imp, rds_snw, k_lo, k_hi, imp_cnc, overrides=None, quiet=False):
+    """SSP rows for wavelengths k / 100 um, k = k_lo .. k_hi.
+
+    ``overrides``: the reference's ``test=True`` hook (monte_carlo3D.py:1553-1573) -- constants replacing
+    ssa_ice / ext_cff_mss_ice / g / ssa_imp / ext_cff_mss_imp when present."""
+    overrides = overrides or {}
+    k = np.arange(k_lo, k_hi + 1)
+    wvls = k / 100.0   # == np.around(x, 2) for every x that rounds to k: rint(100 x) / 100
+    warn = None if quiet else {}
+    ice = read_table(ice_file(optics_dir, rds_snw), ('wvl', 'ss_alb', 'ext_cff_mss', 'asm_prm'))
+    ice_v = nearest_pair_interp(ice['wvl'], {'ssa_ice': ice['ss_alb'], 'ext_cff_mss_ice': ice['ext_cff_mss'],
+                                             'g': ice['asm_prm']}, wvls, warn)
+    imp = read_table(impurity_file(optics_dir, fi_imp), ('wvl', 'ss_alb', 'ext_cff_mss'))
+    imp_v = nearest_pair_interp(imp['wvl'], {'ssa_imp': imp['ss_alb'], 'ext_cff_mss_imp': imp['ext_cff_mss']},
+                                wvls, warn)
+    vals = dict(ice_v)
+    vals.update(imp_v)
+    for name in ('ssa_ice', 'ext_cff_mss_ice', 'g', 'ssa_imp', 'ext_cff_mss_imp'):
+        if name in overrides and overrides[name] is not None:
+            vals[name] = overrides[name] * np.ones(len(wvls))       # monte_carlo3D.py:1554-1573
+    return derive_rows(wvls, vals, imp_cnc)
+
+
+def derive_rows(wvls, vals, imp_cnc):
+    """monte_carlo3D.py:1575-1588: combined extinction and impurity-extinction probability."""
+    ext_ice, ext_imp = vals['ext_cff_mss_ice'], vals['ext_cff_mss_imp']
+    rows = np.zeros(len(wvls), dtype=ROW_DTYPE)
+    rows['wvl_um'] = wvls
+    rows['ssa_ice'] = vals['ssa_ice']
+    rows['ssa_imp'] = vals['ssa_imp']
+    rows['g'] = vals['g']
+    rows['ext_cff_mss'] = ext_ice * (1 - imp_cnc) + ext_imp * imp_cnc
+    rows['p_ext_imp'] = (imp_cnc * ext_imp) / (imp_cnc * ext_imp + (1 - imp_cnc) * ext_ice)
+    return rows
+
+
+def snow_depth(rows, tau_tot, rho_snw):
+    """monte_carlo3D.py:1612."""
+    return tau_tot / (rows['ext_cff_mss'] * rho_snw)
