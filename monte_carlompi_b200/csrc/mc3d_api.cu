@@ -14,6 +14,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
 #include <new>
@@ -27,8 +28,7 @@
 
 namespace mc3d {
 cudaError_t launch_walk(const WalkParams &P, bool impurity, int block_threads, int blocks_per_sm, int grid,
-                        cudaStream_t stream);
-int walk_occupancy(bool impurity, int block_threads, int blocks_per_sm, int n_rows);
+                        cudaStream_t stream, int *occupancy);
 cudaError_t launch_finalize(const FinalizeParams &P, int sm_count, cudaStream_t stream);
 cudaError_t launch_replay(const ReplayParams &P, cudaStream_t stream);
 }  // namespace mc3d
@@ -107,7 +107,7 @@ int load_nccl()
 namespace {
 
 constexpr uint64_t CHUNK_PHOTONS = 1ull << 26;   // raw results: 32 B/photon -> 2 GiB per chunk buffer
-constexpr int N_SLOTS = 2;
+constexpr int N_SLOTS = 8;
 
 template <typename T>
 struct DevBuf {
@@ -146,6 +146,7 @@ struct Slot {
     DevRow *host_rows = nullptr;            // pinned staging for the row upload
     double *host_edges = nullptr;
     size_t host_rows_cap = 0, host_edges_cap = 0;
+    cudaStream_t stream = nullptr;          // each slot has its own stream: two calls in flight overlap on the GPU
     std::vector<cudaEvent_t> ev;            // pairs (begin, end) around walk+finalize of each chunk
     // pending call
     bool busy = false;
@@ -158,7 +159,6 @@ struct Slot {
 struct Device {
     int id = 0;
     int sm_count = 0, clock_khz = 0;
-    cudaStream_t stream = nullptr;
     Slot slot[N_SLOTS];
 };
 
@@ -279,7 +279,7 @@ static int init_device(Device &d, int id)
                     prop.minor);
     d.sm_count = prop.multiProcessorCount;
     CUDA_TRY(cudaDeviceGetAttribute(&d.clock_khz, cudaDevAttrClockRate, id));
-    CUDA_TRY(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+    for (Slot &s : d.slot) CUDA_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     return MC3D_OK;
 }
 
@@ -369,8 +369,8 @@ int mc3d_destroy(mc3d_ctx *ctx)
         if (ctx->comms[k] && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comms[k]);
     for (Device &d : ctx->devs) {
         if (cudaSetDevice(d.id) != cudaSuccess) continue;
-        if (d.stream) cudaStreamSynchronize(d.stream);
         for (Slot &s : d.slot) {
+            if (s.stream) cudaStreamSynchronize(s.stream);
             s.rows.release(); s.edges.release(); s.counters.release(); s.raw.release(); s.condition.release();
             s.wvl_row.release(); s.theta_n.release(); s.phi_n.release(); s.path_length.release();
             s.n_scat.release(); s.tally.release();
@@ -378,8 +378,8 @@ int mc3d_destroy(mc3d_ctx *ctx)
             if (s.host_rows) cudaFreeHost(s.host_rows);
             if (s.host_edges) cudaFreeHost(s.host_edges);
             for (cudaEvent_t e : s.ev) cudaEventDestroy(e);
+            if (s.stream) cudaStreamDestroy(s.stream);
         }
-        if (d.stream) cudaStreamDestroy(d.stream);
     }
     delete ctx;
     return MC3D_OK;
@@ -439,7 +439,7 @@ int mc3d_run_async(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, const mc3d
 {
     int rc = check_ctx(ctx);
     if (rc) return rc;
-    if (slot_idx < 0 || slot_idx >= N_SLOTS) return fail(MC3D_EINVAL, "slot must be 0 or 1");
+    if (slot_idx < 0 || slot_idx >= N_SLOTS) return fail(MC3D_EINVAL, "slot must be in [0, %d)", N_SLOTS);
     rc = validate_run(P, table, n_rows);
     if (rc) return rc;
     for (Device &d : ctx->devs)
@@ -535,13 +535,17 @@ int mc3d_run_async(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, const mc3d
         } else {
             s.host_edges[0] = 0.0;
         }
-        CUDA_TRY(cudaMemcpyAsync(s.rows.p, s.host_rows, n_rows * sizeof(DevRow), cudaMemcpyHostToDevice, d.stream));
-        CUDA_TRY(cudaMemcpyAsync(s.edges.p, s.host_edges, (P->n_theta_bins + 1) * sizeof(double), cudaMemcpyHostToDevice, d.stream));
-        CUDA_TRY(cudaMemsetAsync(s.counters.p, 0, std::max(n_chunks, 1) * sizeof(uint32_t), d.stream));
-        CUDA_TRY(cudaMemsetAsync(s.tally.p, 0, (tally_len + 1) * sizeof(unsigned long long), d.stream));
+        CUDA_TRY(cudaMemcpyAsync(s.rows.p, s.host_rows, n_rows * sizeof(DevRow), cudaMemcpyHostToDevice, s.stream));
+        CUDA_TRY(cudaMemcpyAsync(s.edges.p, s.host_edges, (P->n_theta_bins + 1) * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+        CUDA_TRY(cudaMemsetAsync(s.counters.p, 0, std::max(n_chunks, 1) * sizeof(uint32_t), s.stream));
+        CUDA_TRY(cudaMemsetAsync(s.tally.p, 0, (tally_len + 1) * sizeof(unsigned long long), s.stream));
 
         // ---- launch configuration: persistent grid, SM count x resident blocks
-        int resident = walk_occupancy(impurity, ctx->block_threads, ctx->blocks_per_sm, n_rows);
+        int resident = 0;
+        {
+            WalkParams Wq = W;
+            CUDA_TRY(launch_walk(Wq, impurity, ctx->block_threads, ctx->blocks_per_sm, 0, s.stream, &resident));
+        }
         if (resident < 1) return fail(MC3D_ECUDA, "walk kernel does not fit on an SM (block %d, rows %d)", ctx->block_threads, n_rows);
         resident = std::min(resident, ctx->blocks_per_sm);
         st.grid_blocks = d.sm_count * resident;
@@ -557,8 +561,8 @@ int mc3d_run_async(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, const mc3d
             Wc.raw = s.raw.p;
             const int want = (int)((c_cnt + ctx->block_threads - 1) / ctx->block_threads);
             const int grid = std::max(1, std::min(st.grid_blocks, want));
-            CUDA_TRY(cudaEventRecord(s.ev[2 * c], d.stream));
-            CUDA_TRY(launch_walk(Wc, impurity, ctx->block_threads, ctx->blocks_per_sm, grid, d.stream));
+            CUDA_TRY(cudaEventRecord(s.ev[2 * c], s.stream));
+            CUDA_TRY(launch_walk(Wc, impurity, ctx->block_threads, ctx->blocks_per_sm, grid, s.stream, nullptr));
             FinalizeParams F;
             memset(&F, 0, sizeof F);
             F.raw = s.raw.p;
@@ -577,13 +581,13 @@ int mc3d_run_async(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, const mc3d
             }
             F.tally = s.tally.p;
             F.n_events = s.tally.p + tally_len;
-            CUDA_TRY(launch_finalize(F, d.sm_count, d.stream));
-            CUDA_TRY(cudaEventRecord(s.ev[2 * c + 1], d.stream));
+            CUDA_TRY(launch_finalize(F, d.sm_count, s.stream));
+            CUDA_TRY(cudaEventRecord(s.ev[2 * c + 1], s.stream));
             if (want_rec) {
                 const uint64_t o = off + c_off;
 #define COPY_COL(col, T)                                                                                       \
     if (rec->col)                                                                                              \
-        CUDA_TRY(cudaMemcpyAsync(rec->col + o, s.col.p, (size_t)c_cnt * sizeof(T), cudaMemcpyDeviceToHost, d.stream))
+        CUDA_TRY(cudaMemcpyAsync(rec->col + o, s.col.p, (size_t)c_cnt * sizeof(T), cudaMemcpyDeviceToHost, s.stream))
                 COPY_COL(condition, uint8_t);
                 COPY_COL(wvl_row, int16_t);
                 COPY_COL(theta_n, float);
@@ -606,7 +610,7 @@ int mc3d_run_async(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, const mc3d
         for (int k = 0; k < n_dev; ++k) {
             Device &d = ctx->devs[k];
             Slot &s = d.slot[slot_idx];
-            NCCL_TRY(g_nccl.Reduce(s.tally.p, s.tally.p, tally_len + 1, ncclUint64, ncclSum, 0, ctx->comms[k], d.stream));
+            NCCL_TRY(g_nccl.Reduce(s.tally.p, s.tally.p, tally_len + 1, ncclUint64, ncclSum, 0, ctx->comms[k], s.stream));
         }
         NCCL_TRY(g_nccl.GroupEnd());
     }
@@ -614,7 +618,7 @@ int mc3d_run_async(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, const mc3d
         Device &d = ctx->devs[0];
         Slot &s = d.slot[slot_idx];
         CUDA_TRY(cudaSetDevice(d.id));
-        CUDA_TRY(cudaMemcpyAsync(s.host_tally, s.tally.p, (tally_len + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, d.stream));
+        CUDA_TRY(cudaMemcpyAsync(s.host_tally, s.tally.p, (tally_len + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
     }
     return MC3D_OK;
 }
@@ -623,7 +627,7 @@ int mc3d_wait(mc3d_ctx *ctx, int slot_idx, mc3d_stats *stats)
 {
     int rc = check_ctx(ctx);
     if (rc) return rc;
-    if (slot_idx < 0 || slot_idx >= N_SLOTS) return fail(MC3D_EINVAL, "slot must be 0 or 1");
+    if (slot_idx < 0 || slot_idx >= N_SLOTS) return fail(MC3D_EINVAL, "slot must be in [0, %d)", N_SLOTS);
     if (!ctx->devs[0].slot[slot_idx].busy) return fail(MC3D_EINVAL, "slot %d has no call in flight", slot_idx);
     mc3d_stats &st = ctx->pending_stats[slot_idx];
     double kernel_ms = 0.0;
@@ -631,7 +635,7 @@ int mc3d_wait(mc3d_ctx *ctx, int slot_idx, mc3d_stats *stats)
     for (Device &d : ctx->devs) {
         Slot &s = d.slot[slot_idx];
         cudaSetDevice(d.id);
-        cudaError_t e = cudaStreamSynchronize(d.stream);
+        cudaError_t e = cudaStreamSynchronize(s.stream);
         s.busy = false;
         if (e != cudaSuccess) {
             if (!first_err) first_err = fail(MC3D_ECUDA, "device %d: %s", d.id, cudaGetErrorString(e));
@@ -660,7 +664,7 @@ int mc3d_run(mc3d_ctx *ctx, const mc3d_params *params, const mc3d_ssp_row *table
 {
     int rc = mc3d_run_async(ctx, 0, params, table, n_rows, seed, photon_begin, n_photon, records, tally, stats);
     if (rc) {
-        if (ctx) for (Device &d : ctx->devs) { cudaSetDevice(d.id); cudaStreamSynchronize(d.stream); d.slot[0].busy = false; }
+        if (ctx) for (Device &d : ctx->devs) { cudaSetDevice(d.id); cudaStreamSynchronize(d.slot[0].stream); d.slot[0].busy = false; }
         return rc;
     }
     return mc3d_wait(ctx, 0, stats);
@@ -674,15 +678,16 @@ int mc3d_reduce_tally(mc3d_ctx *ctx, uint64_t *tally, uint64_t n, int root)
     if (ctx->world == 1) return MC3D_OK;
     if (root < 0 || root >= ctx->world) return fail(MC3D_EINVAL, "root %d out of range", root);
     Device &d = ctx->devs[0];
+    cudaStream_t stream0 = d.slot[0].stream;
     CUDA_TRY(cudaSetDevice(d.id));
     unsigned long long *buf = nullptr;
     CUDA_TRY(cudaMalloc((void **)&buf, std::max<uint64_t>(n, 1) * sizeof(unsigned long long)));
-    cudaError_t e = cudaMemcpyAsync(buf, tally, n * sizeof(uint64_t), cudaMemcpyHostToDevice, d.stream);
+    cudaError_t e = cudaMemcpyAsync(buf, tally, n * sizeof(uint64_t), cudaMemcpyHostToDevice, stream0);
     ncclResult_t r = ncclSuccess;
-    if (e == cudaSuccess) r = g_nccl.Reduce(buf, buf, n, ncclUint64, ncclSum, root, ctx->comms[0], d.stream);
+    if (e == cudaSuccess) r = g_nccl.Reduce(buf, buf, n, ncclUint64, ncclSum, root, ctx->comms[0], stream0);
     if (e == cudaSuccess && r == ncclSuccess && ctx->rank == root)
-        e = cudaMemcpyAsync(tally, buf, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, d.stream);
-    cudaError_t e2 = cudaStreamSynchronize(d.stream);
+        e = cudaMemcpyAsync(tally, buf, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, stream0);
+    cudaError_t e2 = cudaStreamSynchronize(stream0);
     cudaFree(buf);
     if (r != ncclSuccess) return fail(MC3D_ENCCL, "ncclReduce failed: %s", g_nccl.GetErrorString(r));
     if (e != cudaSuccess) return fail(MC3D_ECUDA, "tally copy failed: %s", cudaGetErrorString(e));
@@ -708,6 +713,7 @@ int mc3d_replay(mc3d_ctx *ctx, const mc3d_params *P, uint64_t n, const double *w
     const uint64_t n_stream = (uint64_t)offsets[n];
     if (n_stream && !stream) return fail(MC3D_EINVAL, "stream is null");
     Device &d = ctx->devs[0];
+    cudaStream_t stream0 = d.slot[0].stream;
     CUDA_TRY(cudaSetDevice(d.id));
 
     // one arena: 6 + 3 per-photon double inputs, offsets, stream, then outputs
@@ -731,11 +737,11 @@ int mc3d_replay(mc3d_ctx *ctx, const mc3d_params *P, uint64_t n, const double *w
     TRY_OR_CLEAN(cudaMalloc((void **)&d_cond, n * sizeof(int)));
     const double *ins[6] = {wvl, ssa_ice, ssa_imp, g, ext_cff_mss, p_ext_imp};
     for (int k = 0; k < 6; ++k)
-        TRY_OR_CLEAN(cudaMemcpyAsync(d_in + k * n, ins[k], n * sizeof(double), cudaMemcpyHostToDevice, d.stream));
-    TRY_OR_CLEAN(cudaMemcpyAsync(d_in + 6 * n, init_draws, 3 * n * sizeof(double), cudaMemcpyHostToDevice, d.stream));
-    TRY_OR_CLEAN(cudaMemcpyAsync(d_off, offsets, (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, d.stream));
+        TRY_OR_CLEAN(cudaMemcpyAsync(d_in + k * n, ins[k], n * sizeof(double), cudaMemcpyHostToDevice, stream0));
+    TRY_OR_CLEAN(cudaMemcpyAsync(d_in + 6 * n, init_draws, 3 * n * sizeof(double), cudaMemcpyHostToDevice, stream0));
+    TRY_OR_CLEAN(cudaMemcpyAsync(d_off, offsets, (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, stream0));
     if (n_stream)
-        TRY_OR_CLEAN(cudaMemcpyAsync(d_stream, stream, n_stream * sizeof(double), cudaMemcpyHostToDevice, d.stream));
+        TRY_OR_CLEAN(cudaMemcpyAsync(d_stream, stream, n_stream * sizeof(double), cudaMemcpyHostToDevice, stream0));
 
     ReplayParams R;
     memset(&R, 0, sizeof R);
@@ -749,11 +755,11 @@ int mc3d_replay(mc3d_ctx *ctx, const mc3d_params *P, uint64_t n, const double *w
     R.wvn = d_outd; R.theta_n = d_outd + n; R.phi_n = d_outd + 2 * n; R.path_length = d_outd + 3 * n;
     R.snow_depth = d_outd + 4 * n;
     R.n_scat = d_outl; R.consumed = d_outl + n;
-    TRY_OR_CLEAN(launch_replay(R, d.stream));
+    TRY_OR_CLEAN(launch_replay(R, stream0));
 
     std::vector<long long> consumed(n);
 #define BACK(dst, src, T) \
-    if (dst) TRY_OR_CLEAN(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyDeviceToHost, d.stream))
+    if (dst) TRY_OR_CLEAN(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyDeviceToHost, stream0))
     BACK(out->condition, d_cond, int);
     BACK(out->wvn, R.wvn, double);
     BACK(out->theta_n, R.theta_n, double);
@@ -763,7 +769,7 @@ int mc3d_replay(mc3d_ctx *ctx, const mc3d_params *P, uint64_t n, const double *w
     BACK(out->n_scat, R.n_scat, long long);
     BACK(consumed.data(), R.consumed, long long);
 #undef BACK
-    TRY_OR_CLEAN(cudaStreamSynchronize(d.stream));
+    TRY_OR_CLEAN(cudaStreamSynchronize(stream0));
 #undef TRY_OR_CLEAN
     cleanup();
     uint64_t mism = 0;

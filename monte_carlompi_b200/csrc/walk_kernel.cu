@@ -22,20 +22,23 @@ namespace mc3d {
 
 constexpr int RING = 64;  // entries per warp; a refill adds at most 32 to fewer than 32 leftovers
 
+// Fresh photons prepared by the whole warp, waiting for a lane (first event already taken).
 struct WarpRing {
-    uint32_t pid[RING];   // photon offset in this launch
-    uint32_t row[RING];   // SSP row
-    float dtau[RING];     // free path of the first event
+    uint32_t pid[RING];    // photon offset in this launch
+    uint32_t row[RING];    // SSP row
+    float dtau[RING];      // free path of the first event
 };
 
 // Walk state of the photon a lane is carrying.
 struct Lane {
     float z, ux, uy, uz;
     float path_lo, path_hi;   // path in optical-depth units: path_hi + path_lo (flushed every 256 events)
-    uint32_t i;               // events completed
+    uint32_t i;               // events completed; 0 = the lane carries no photon
     uint32_t pid;             // photon offset in this launch
     uint32_t row;
     uint32_t plo, phi;        // global photon id (Philox counter words 2, 3)
+    uint32_t w3;              // absorption word of the last event (for the deferred fine test)
+    bool imp;                 // last event's extinction was by the impurity
     // row constants
     float one_m_g, one_m_g2, two_g;
     uint32_t flip, t_hi;
@@ -82,83 +85,12 @@ __device__ __forceinline__ bool species_is_impurity(const WalkParams &P, const D
     return w <= R.s_last;
 }
 
-// 40-bit absorption test u >= ssa (monte_carlo3D.py:1461), w3 = high 32 bits, low byte of w1 = low 8 bits
-__device__ __forceinline__ bool absorbed40(uint32_t w3, uint32_t w1, uint32_t t_hi, uint32_t t_lo)
-{
-    return w3 > t_hi || (w3 == t_hi && (w1 & 0xffu) >= t_lo);
-}
-
 constexpr uint32_t ALIVE = 0;
 
-// State handed to / returned from the rarely executed boundary code (kept out of the hot loop's registers).
-struct SlowIO {
-    float z, ux, uy, uz, path_add;
-    uint32_t i;
-};
-
-// Event io.i just moved the photon from z_prev to io.z by dtau and one of "z > 0", "z < -tau_tot", "absorption
-// word at/above the coarse threshold" holds.  Resolves the reference's termination chain
-// monte_carlo3D.py:1390-1466 in its order; on a Lambertian-bottom reflection it also performs the NEXT event
-// (1238-1250: cosine-law rejection sampling about +z) so the hot loop never carries a bottom_reflection flag.
-// Returns the condition (0 = keep walking).
-template <bool IMP>
-__device__ __forceinline__ uint32_t slow_path(const WalkParams &P, const DevRow *rows, uint32_t row, SlowIO *io,
-                                           float z_prev, float dtau, uint32_t w1, uint32_t w3, bool imp,
-                                           uint32_t plo, uint32_t phi)
+// The scattering part of event L.i+1 given its Philox block w: HG deflection, azimuth, rotation, move.
+// monte_carlo3D.py:1252-1281 (deflection + rotation), 1352 (move), 1372 (path).  No termination logic.
+__device__ __forceinline__ void scatter_and_move(Lane &L, const uint4 w)
 {
-    const DevRow &R = rows[row];
-    float z = io->z;
-    io->path_add = 0.0f;
-    if (z > 0.0f) {   // reflected (1390-1397): remove the part of the step above the surface
-        io->path_add = -(z * dtau) / (z - z_prev);
-        return 1u;
-    }
-    if (z < P.neg_tau_tot) {   // 1399-1459
-        io->path_add = -((z + P.tau_tot) * dtau) / (z - z_prev);
-        io->z = z = P.neg_tau_tot;
-        const uint32_t exit_cond = (io->i == 1u) ? 3u : 2u;
-        if (!P.lambert_bottom) return exit_cond;
-        const uint4 b = philox4x32_10(io->i, TAG_LAMBERT, plo, phi, P.rk);
-        if ((long long)b.x > P.refl_thr) return exit_cond;
-        // ---- reflected by the Lambertian bottom: event i+1 happens here ----
-        const uint32_t i2 = io->i + 1u;
-        io->i = i2;
-        const uint4 w = philox4x32_10(i2, TAG_EVENT, plo, phi, P.rk);
-        float ct, st;
-        for (uint32_t j = 0;; ++j) {
-            const uint4 a = philox4x32_10(i2, TAG_LAMBERT | ((1u + (j >> 1)) << 8), plo, phi, P.rk);
-            const float u_t = u32_to_unit((j & 1u) ? a.z : a.x);
-            const float r1 = u32_to_unit((j & 1u) ? a.w : a.y);
-            float s_, c_;
-            sincosf(1.5707963267948966f * u_t, &s_, &c_);
-            if (r1 < 2.0f * s_ * c_) { ct = c_; st = s_; break; }
-        }
-        float cp, sp;
-        azimuth(w.y, cp, sp);
-        io->ux = st * cp; io->uy = st * sp; io->uz = ct;   // muz_0 == 1 branch, 1262-1265
-        const float dt2 = free_path(w.z);
-        z = fmaf(dt2, ct, P.neg_tau_tot);
-        io->z = z;
-        io->path_add += dt2;
-        const bool imp2 = IMP ? species_is_impurity(P, R, i2, plo, phi) : false;
-        if (z > 0.0f) {
-            io->path_add += -(z * dt2) / (z - P.neg_tau_tot);
-            return 1u;
-        }
-        if (absorbed40(w.w, w.y, imp2 ? R.ti_hi : R.t_hi, imp2 ? R.ti_lo : R.t_lo)) return imp2 ? 5u : 4u;
-        return ALIVE;
-    }
-    if (absorbed40(w3, w1, imp ? R.ti_hi : R.t_hi, imp ? R.ti_lo : R.t_lo)) return imp ? 5u : 4u;   // 1461-1466
-    return ALIVE;
-}
-
-// One scattering event (i >= 2) of the photon in L: monte_carlo3D.py:1212-1466 for the sphere/HG branch.
-// Returns the condition (0 = still walking).
-template <bool IMP>
-__device__ __forceinline__ uint32_t event_step(const WalkParams &P, const DevRow *rows, Lane &L)
-{
-    L.i += 1u;
-    const uint4 w = philox4x32_10(L.i, TAG_EVENT, L.plo, L.phi, P.rk);
     // Henyey-Greenstein inverse CDF (790-800) in a cancellation-free form:
     //   D = 1 - g + 2 g r,  s = (1 - g^2)/D,  1 - cos = (1 - g)(1 - r)(s + 1 - g)/D,  sin^2 = (1 - cos)(1 + cos)
     const float r = u32_to_unit(w.x ^ L.flip);
@@ -169,41 +101,90 @@ __device__ __forceinline__ uint32_t event_step(const WalkParams &P, const DevRow
     const float st = sqrt_fast(omc * (2.0f - omc));
     float cp, sp;
     azimuth(w.y, cp, sp);
-    // rotate the direction cosines (1262-1281)
     const float d2 = fmaf(L.ux, L.ux, L.uy * L.uy);
     float nx, ny, nz;
-    if (d2 < 1e-24f) {   // travelling along +-z: the reference's muz_0 == +-1 branches
+    if (d2 < 1e-24f) {   // travelling along +-z: the reference's muz_0 == +-1 branches (1262-1269)
         const float sg = L.uz > 0.0f ? 1.0f : -1.0f;
         nx = st * cp; ny = sg * st * sp; nz = sg * ct;
-    } else {
-        const float inv_d = rsqrt_fast(d2), a = st * inv_d;
+    } else {             // 1270-1281
+        const float a = st * rsqrt_fast(d2);
         const float uzc = L.uz * cp;
         nx = fmaf(a, fmaf(L.ux, uzc, -L.uy * sp), L.ux * ct);
         ny = fmaf(a, fmaf(L.uy, uzc, L.ux * sp), L.uy * ct);
         nz = fmaf(-(d2 * a), cp, L.uz * ct);
     }
     L.ux = nx; L.uy = ny; L.uz = nz;
-    // free path (1014), move (1352), path length (1372)
     const float dtau = free_path(w.z);
-    const float z_prev = L.z;
-    L.z = fmaf(dtau, nz, z_prev);
+    L.z = fmaf(dtau, nz, L.z);
     L.path_lo += dtau;
-    bool imp = false;
-    uint32_t thi = L.t_hi;
-    if (IMP) {
-        const DevRow &R = rows[L.row];
-        imp = species_is_impurity(P, R, L.i, L.plo, L.phi);
-        thi = imp ? R.ti_hi : thi;
-    }
+    L.w3 = w.w;
+}
+
+// "Something may have happened": the photon left the slab, may have been absorbed (coarse 32-bit test), or is
+// due for its periodic renormalisation.  Everything behind this predicate is resolved later, by resolve().
+__device__ __forceinline__ bool needs_attention(const WalkParams &P, const Lane &L, uint32_t thi)
+{
+    return L.z > 0.0f || L.z < P.neg_tau_tot || L.w3 >= thi || (L.i & 255u) == 0u;
+}
+
+// Resolve the reference's termination chain monte_carlo3D.py:1390-1466, in its order, for the event L.i that
+// just moved the photon to L.z along L.uz.  Executed by all lanes of a warp that need it at once (deferred), so it
+// is off the hot path.  On a Lambertian-bottom reflection it also performs the NEXT event (1238-1250: cosine-law
+// rejection sampling about +z) so that the hot loop never carries a bottom_reflection flag.
+// Returns the condition (0 = keep walking; the lane's state is then ready for the next event).
+template <bool IMP>
+__device__ __forceinline__ uint32_t resolve(const WalkParams &P, const DevRow *rows, Lane &L)
+{
+    const DevRow &R = rows[L.row];
     uint32_t cond = ALIVE;
-    if (L.z > 0.0f || L.z < P.neg_tau_tot || w.w >= thi) {
-        SlowIO io;
-        io.z = L.z; io.ux = L.ux; io.uy = L.uy; io.uz = L.uz; io.i = L.i;
-        cond = slow_path<IMP>(P, rows, L.row, &io, z_prev, dtau, w.y, w.w, imp, L.plo, L.phi);
-        L.z = io.z; L.ux = io.ux; L.uy = io.uy; L.uz = io.uz; L.i = io.i;
-        L.path_lo += io.path_add;
+    if (L.z > 0.0f) {   // reflected (1390-1397); z - z_prev = dtau muz, so the overshoot path is z / muz
+        L.path_lo -= __fdividef(L.z, L.uz);
+        cond = 1u;
+    } else if (L.z < P.neg_tau_tot) {   // 1399-1459
+        L.path_lo -= __fdividef(L.z + P.tau_tot, L.uz);
+        L.z = P.neg_tau_tot;
+        cond = (L.i == 1u) ? 3u : 2u;
+        if (P.lambert_bottom) {
+            const uint4 b = philox4x32_10(L.i, TAG_LAMBERT, L.plo, L.phi, P.rk);
+            if ((long long)b.x <= P.refl_thr) {
+                // ---- reflected by the Lambertian bottom: event i+1 happens here ----
+                L.i += 1u;
+                const uint4 w = philox4x32_10(L.i, TAG_EVENT, L.plo, L.phi, P.rk);
+                float ct, st;
+                for (uint32_t j = 0;; ++j) {
+                    const uint4 a = philox4x32_10(L.i, TAG_LAMBERT | ((1u + (j >> 1)) << 8), L.plo, L.phi, P.rk);
+                    const float u_t = u32_to_unit((j & 1u) ? a.z : a.x);
+                    const float r1 = u32_to_unit((j & 1u) ? a.w : a.y);
+                    float s_, c_;
+                    sincosf(1.5707963267948966f * u_t, &s_, &c_);
+                    if (r1 < 2.0f * s_ * c_) { ct = c_; st = s_; break; }
+                }
+                float cp, sp;
+                azimuth(w.y, cp, sp);
+                L.ux = st * cp; L.uy = st * sp; L.uz = ct;   // muz_0 == 1 branch, 1262-1265
+                const float dt2 = free_path(w.z);
+                L.z = fmaf(dt2, ct, P.neg_tau_tot);
+                L.path_lo += dt2;
+                L.w3 = w.w;
+                L.imp = IMP ? species_is_impurity(P, R, L.i, L.plo, L.phi) : false;
+                cond = ALIVE;
+                if (L.z > 0.0f) {
+                    L.path_lo -= __fdividef(L.z, L.uz);
+                    cond = 1u;
+                }
+            }
+        }
     }
-    if ((L.i & 255u) == 0u) {   // keyed on the photon's own event count -> independent of scheduling
+    if (cond == ALIVE) {   // 1461-1466: absorbed iff the 40-bit variate (w3 << 8 | low byte of w1) >= T40
+        const uint32_t t_hi = L.imp ? R.ti_hi : R.t_hi, t_lo = L.imp ? R.ti_lo : R.t_lo;
+        bool absorbed = L.w3 > t_hi;
+        if (L.w3 == t_hi) {   // probability 2^-32: regenerate the event's block for the low byte
+            const uint4 w = philox4x32_10(L.i, TAG_EVENT, L.plo, L.phi, P.rk);
+            absorbed = (w.y & 0xffu) >= t_lo;
+        }
+        if (absorbed) cond = L.imp ? 5u : 4u;
+    }
+    if (cond == ALIVE && (L.i & 255u) == 0u) {   // keyed on the photon's own event count: scheduling independent
         const float rn = rsqrt_fast(fmaf(L.ux, L.ux, fmaf(L.uy, L.uy, L.uz * L.uz)));
         L.ux *= rn; L.uy *= rn; L.uz *= rn;
         L.path_hi += L.path_lo;
@@ -221,7 +202,7 @@ __device__ __forceinline__ void load_row_constants(Lane &L, const DevRow &R)
 // survivors to the warp's ring.  All 32 lanes execute this.  Returns 0 when the photon range is exhausted.
 template <bool IMP>
 __device__ __forceinline__ uint32_t prepare_batch(const WalkParams &P, const DevRow *rows, WarpRing &Q,
-                                               uint32_t &ring_tail, uint32_t lane)
+                                                  uint32_t &ring_tail, uint32_t lane)
 {
     uint32_t base = 0;
     if (lane == 0) base = atomicAdd(P.counter, 32u);
@@ -247,22 +228,23 @@ __device__ __forceinline__ uint32_t prepare_batch(const WalkParams &P, const Dev
         const bool imp = IMP ? species_is_impurity(P, R, 1u, plo, phi) : false;
         survive = true;
         if (z1 < P.neg_tau_tot || w.w >= (imp ? R.ti_hi : R.t_hi)) {
-            SlowIO io;
-            io.z = z1; io.ux = P.mu0x; io.uy = 0.0f; io.uz = P.mu0z; io.i = 1u;
-            uint32_t cond = slow_path<IMP>(P, rows, row, &io, 0.0f, dtau, w.y, w.w, imp, plo, phi);
-            if (cond == ALIVE && io.i != 1u) {
+            Lane L;
+            L.z = z1; L.ux = P.mu0x; L.uy = 0.0f; L.uz = P.mu0z; L.i = 1u; L.path_lo = dtau; L.path_hi = 0.0f;
+            L.pid = pid; L.row = row; L.plo = plo; L.phi = phi; L.w3 = w.w; L.imp = imp;
+            load_row_constants(L, R);
+            uint32_t cond = resolve<IMP>(P, rows, L);
+            if (cond == ALIVE && L.i != 1u) {
                 // reflected off the Lambertian bottom on its first step and still alive after event 2: it no
                 // longer fits the ring's "fresh photon" format, so it is walked to completion here (thin slabs only)
-                Lane L;
-                L.z = io.z; L.ux = io.ux; L.uy = io.uy; L.uz = io.uz; L.i = io.i;
-                L.path_lo = dtau + io.path_add; L.path_hi = 0.0f;
-                L.pid = pid; L.row = row; L.plo = plo; L.phi = phi;
-                load_row_constants(L, R);
-                do { cond = event_step<IMP>(P, rows, L); } while (cond == ALIVE);
+                do {
+                    L.i += 1u;
+                    scatter_and_move(L, philox4x32_10(L.i, TAG_EVENT, plo, phi, P.rk));
+                    L.imp = IMP ? species_is_impurity(P, R, L.i, plo, phi) : false;
+                    if (needs_attention(P, L, L.imp ? R.ti_hi : L.t_hi)) cond = resolve<IMP>(P, rows, L);
+                } while (cond == ALIVE);
+            }
+            if (cond != ALIVE) {
                 store_raw(P, pid, L.ux, L.uy, L.uz, L.path_hi + L.path_lo, L.i - 1u, cond, row);
-                survive = false;
-            } else if (cond != ALIVE) {
-                store_raw(P, pid, io.ux, io.uy, io.uz, dtau + io.path_add, io.i - 1u, cond, row);
                 survive = false;
             }
         }
@@ -297,52 +279,72 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) walk_kernel(const __grid_co
 
     Lane L;
     L.z = 0.f; L.ux = 0.f; L.uy = 0.f; L.uz = -1.f; L.path_lo = 0.f; L.path_hi = 0.f;
-    L.i = 0; L.pid = 0; L.row = 0; L.plo = 0; L.phi = 0;
+    L.i = 0; L.pid = 0; L.row = 0; L.plo = 0; L.phi = 0; L.w3 = 0; L.imp = false;
     L.one_m_g = 1.f; L.one_m_g2 = 1.f; L.two_g = 0.f; L.flip = 0; L.t_hi = 0;
-    bool alive = false;
+    bool alive = false;                  // false: the lane is waiting (needs attention, or carries no photon)
 
     for (;;) {
-        // ---------------------------------------------------------------- refill (warp-uniform branch)
-        const uint32_t dead = __ballot_sync(0xffffffffu, !alive);
-        if (__popc(dead) >= threshold) {
-            if (exhausted && ring_head == ring_tail) {
-                if (dead == 0xffffffffu) break;
-            } else {
-                const uint32_t need = __popc(dead);
-                while (!exhausted && (ring_tail - ring_head) < need)
-                    if (prepare_batch<IMP>(P, rows, Q, ring_tail, lane) == 0u) exhausted = true;
-                const uint32_t avail = ring_tail - ring_head;
-                if (!alive) {
-                    const uint32_t rank = __popc(dead & ((1u << lane) - 1u));
-                    if (rank < avail) {
-                        const uint32_t slot = (ring_head + rank) & (RING - 1);
-                        L.pid = Q.pid[slot];
-                        L.row = Q.row[slot];
-                        const float dtau = Q.dtau[slot];
-                        load_row_constants(L, rows[L.row]);
-                        L.ux = P.mu0x; L.uy = 0.0f; L.uz = P.mu0z;
-                        L.z = dtau * P.mu0z;
-                        L.path_lo = dtau;
-                        L.path_hi = 0.0f;
-                        L.i = 1u;
-                        const unsigned long long gid = P.photon_begin + L.pid;
-                        L.plo = (uint32_t)gid; L.phi = (uint32_t)(gid >> 32);
+        if (!__all_sync(0xffffffffu, alive)) {
+            // ------------------------------------------------------------ deferred attention + refill
+            const uint32_t waiting = __ballot_sync(0xffffffffu, !alive);
+            if (__popc(waiting) >= threshold) {
+                // 1. lanes whose last event tripped needs_attention(): finish or resume them, all together
+                if (!alive && L.i != 0u) {
+                    const uint32_t cond = resolve<IMP>(P, rows, L);
+                    if (cond != ALIVE) {
+                        store_raw(P, L.pid, L.ux, L.uy, L.uz, L.path_hi + L.path_lo, L.i - 1u, cond, L.row);
+                        L.i = 0u;
+                    } else {
                         alive = true;
                     }
                 }
-                ring_head += min(avail, need);
-                __syncwarp();
-                if (exhausted && ring_head == ring_tail) threshold = 32u;   // only "all lanes done" matters now
-                continue;
+                // 2. lanes without a photon take a fresh one from the ring
+                const uint32_t empty = __ballot_sync(0xffffffffu, !alive);
+                const uint32_t need = __popc(empty);
+                if (need != 0u && !(exhausted && ring_head == ring_tail)) {
+                    while (!exhausted && (ring_tail - ring_head) < need)
+                        if (prepare_batch<IMP>(P, rows, Q, ring_tail, lane) == 0u) exhausted = true;
+                    const uint32_t avail = ring_tail - ring_head;
+                    if (!alive) {
+                        const uint32_t rank = __popc(empty & ((1u << lane) - 1u));
+                        if (rank < avail) {
+                            const uint32_t slot = (ring_head + rank) & (RING - 1);
+                            L.pid = Q.pid[slot];
+                            L.row = Q.row[slot];
+                            const float dtau = Q.dtau[slot];
+                            load_row_constants(L, rows[L.row]);
+                            L.ux = P.mu0x; L.uy = 0.0f; L.uz = P.mu0z;
+                            L.z = dtau * P.mu0z;
+                            L.path_lo = dtau;
+                            L.path_hi = 0.0f;
+                            L.i = 1u;
+                            const unsigned long long gid = P.photon_begin + L.pid;
+                            L.plo = (uint32_t)gid; L.phi = (uint32_t)(gid >> 32);
+                            alive = true;
+                        }
+                    }
+                    ring_head += min(avail, need);
+                    __syncwarp();
+                }
+                if (exhausted && ring_head == ring_tail) {
+                    // nothing left to hand out: from now on every waiting lane is resolved immediately
+                    threshold = 1u;
+                    if (__ballot_sync(0xffffffffu, alive) == 0u) break;
+                }
             }
         }
         // ---------------------------------------------------------------- one scattering event per live lane
         if (alive) {
-            const uint32_t cond = event_step<IMP>(P, rows, L);
-            if (cond != ALIVE) {
-                store_raw(P, L.pid, L.ux, L.uy, L.uz, L.path_hi + L.path_lo, L.i - 1u, cond, L.row);
-                alive = false;
+            const uint4 w = philox4x32_10(L.i + 1u, TAG_EVENT, L.plo, L.phi, P.rk);
+            L.i += 1u;
+            scatter_and_move(L, w);
+            uint32_t thi = L.t_hi;
+            if (IMP) {
+                const DevRow &R = rows[L.row];
+                L.imp = species_is_impurity(P, R, L.i, L.plo, L.phi);
+                thi = L.imp ? R.ti_hi : thi;
             }
+            alive = !needs_attention(P, L, thi);
         }
     }
 }
@@ -355,58 +357,46 @@ size_t walk_smem_bytes(int n_rows, int block_threads)
 }
 
 template <bool IMP, int BLOCK, int MIN_BLOCKS>
-static cudaError_t launch_one(const WalkParams &P, int grid, cudaStream_t stream)
+static cudaError_t launch_one(const WalkParams &P, int grid, cudaStream_t stream, int *occupancy)
 {
     const size_t smem = walk_smem_bytes(P.n_rows, BLOCK);
     auto kern = walk_kernel<IMP, BLOCK, MIN_BLOCKS>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    if (occupancy) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occupancy, kern, BLOCK, smem);
     kern<<<grid, BLOCK, smem, stream>>>(P);
     return cudaGetLastError();
 }
 
-// block_threads in {128, 256, 512}; blocks_per_sm is the occupancy target the variant was compiled for
-cudaError_t launch_walk(const WalkParams &P, bool impurity, int block_threads, int blocks_per_sm, int grid,
-                        cudaStream_t stream)
+template <int BLOCK, int MIN_BLOCKS>
+static cudaError_t launch_variant(const WalkParams &P, bool impurity, int grid, cudaStream_t stream, int *occupancy)
 {
-    const int warps_per_sm = block_threads / 32 * blocks_per_sm;
-#define MC3D_PICK(B, M)                                                    \
-    return impurity ? launch_one<true, B, M>(P, grid, stream) : launch_one<false, B, M>(P, grid, stream)
-    if (block_threads == 128) {
-        if (warps_per_sm <= 32) { MC3D_PICK(128, 8); } else if (warps_per_sm <= 40) { MC3D_PICK(128, 10); } else { MC3D_PICK(128, 12); }
-    } else if (block_threads == 256) {
-        if (warps_per_sm <= 32) { MC3D_PICK(256, 4); } else if (warps_per_sm <= 40) { MC3D_PICK(256, 5); } else { MC3D_PICK(256, 6); }
-    } else if (block_threads == 512) {
-        if (warps_per_sm <= 32) { MC3D_PICK(512, 2); } else { MC3D_PICK(512, 3); }
-    }
-#undef MC3D_PICK
-    return cudaErrorInvalidValue;
+    return impurity ? launch_one<true, BLOCK, MIN_BLOCKS>(P, grid, stream, occupancy)
+                    : launch_one<false, BLOCK, MIN_BLOCKS>(P, grid, stream, occupancy);
 }
 
-int walk_occupancy(bool impurity, int block_threads, int blocks_per_sm, int n_rows)
+// block_threads in {128, 256, 512}; blocks_per_sm is the occupancy target the variant is compiled for
+// (64 / 48 / 40 registers per thread for <= 32 / 40 / 48 resident warps per SM).
+// With `occupancy` non-null nothing is launched; the resident blocks per SM are returned through it.
+cudaError_t launch_walk(const WalkParams &P, bool impurity, int block_threads, int blocks_per_sm, int grid,
+                        cudaStream_t stream, int *occupancy)
 {
-    int nb = 0;
-    const size_t smem = walk_smem_bytes(n_rows, block_threads);
-#define MC3D_OCC(B, M)                                                                                            \
-    do {                                                                                                            \
-        if (impurity) {                                                                                             \
-            cudaFuncSetAttribute(walk_kernel<true, B, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, walk_kernel<true, B, M>, B, smem);                   \
-        } else {                                                                                                    \
-            cudaFuncSetAttribute(walk_kernel<false, B, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, walk_kernel<false, B, M>, B, smem);                  \
-        }                                                                                                           \
-    } while (0)
     const int warps_per_sm = block_threads / 32 * blocks_per_sm;
     if (block_threads == 128) {
-        if (warps_per_sm <= 32) MC3D_OCC(128, 8); else if (warps_per_sm <= 40) MC3D_OCC(128, 10); else MC3D_OCC(128, 12);
-    } else if (block_threads == 256) {
-        if (warps_per_sm <= 32) MC3D_OCC(256, 4); else if (warps_per_sm <= 40) MC3D_OCC(256, 5); else MC3D_OCC(256, 6);
-    } else if (block_threads == 512) {
-        if (warps_per_sm <= 32) MC3D_OCC(512, 2); else MC3D_OCC(512, 3);
+        if (warps_per_sm <= 32) return launch_variant<128, 8>(P, impurity, grid, stream, occupancy);
+        if (warps_per_sm <= 40) return launch_variant<128, 10>(P, impurity, grid, stream, occupancy);
+        return launch_variant<128, 12>(P, impurity, grid, stream, occupancy);
     }
-#undef MC3D_OCC
-    return nb;
+    if (block_threads == 256) {
+        if (warps_per_sm <= 32) return launch_variant<256, 4>(P, impurity, grid, stream, occupancy);
+        if (warps_per_sm <= 40) return launch_variant<256, 5>(P, impurity, grid, stream, occupancy);
+        return launch_variant<256, 6>(P, impurity, grid, stream, occupancy);
+    }
+    if (block_threads == 512) {
+        if (warps_per_sm <= 32) return launch_variant<512, 2>(P, impurity, grid, stream, occupancy);
+        return launch_variant<512, 3>(P, impurity, grid, stream, occupancy);
+    }
+    return cudaErrorInvalidValue;
 }
 
 }  // namespace mc3d

@@ -12,6 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libmc3d.so')
 
 N_COND = 8
+N_SLOTS = 8
 FLAG_LAMBERT_BOTTOM = 1
 FLAG_LAMBERT_SURFACE = 2
 ABI_VERSION = 1
@@ -193,7 +194,7 @@ class Context(object):
             _check(self._lib.mc3d_create_rank(C.byref(self._ctx), int(device if device is not None else 0), idbuf,
                                               int(rank), int(world_size)))
             self.rank, self.world_size, self.n_devices = int(rank), int(world_size), 1
-        self._keep = [None, None]
+        self._keep = [None] * N_SLOTS
 
     def close(self):
         if self._ctx is not None and self._ctx.value:

@@ -1,0 +1,256 @@
+"""Drop-in ``MonteCarlo`` for the reference's monte_carloMPI/monte_carlo3D.py -- spheres / Henyey-Greenstein path.
+
+Same driver surface as the reference (monte_carlo3D.py:42-94 constructor + config/flags 1778-1843, ``run``
+1492-1657, ``setup_output`` 96-143): ``MonteCarlo(**model_kwargs).run(n_photon, wvl0, half_width, rds_snw,
+theta_0=..., Lambertian_bottom=..., ...)`` reads ``./config.ini`` and the Mie NetCDF tables, walks ``n_photon``
+photon packets and writes ``<output_dir>/sphere/WVL_FWHM_REFF_NPHOTON_THETA_HG.txt``, then prints the path.
+
+What changed underneath: the Python photon loop (monte_carlo3D.py:1613-1616) and the mpi4py scatter / gather
+(parallelize.py) are replaced by one call into libmc3d.so (hand-written sm_100a CUDA; engine.py is the ctypes
+binding).  Wavelengths are drawn on the GPU from a Philox4x32-10 stream keyed on (seed, photon id), so the
+per-photon SSP arrays of the reference become one small per-wavelength table (ssp.py).
+
+Not carried over (out of scope): aspherical grain shapes / full phase matrices
+(their data files are not part of the reference archive), Lambertian_surface mode, plotting and debug demos.
+Those raise NotImplementedError rather than silently doing something else.
+"""
+import argparse
+import configparser
+import os
+
+import numpy as np
+
+from . import engine, output, ssp
+from .parallelize import Parallel
+
+TWO_PIE = 2 * np.pi
+FOUR_PIE = 4 * np.pi
+
+DEFAULT_N_THETA_BINS = 137   # int(pi * 175 / 4): post_processing.py:331-334, 435-444
+
+
+class MonteCarlo(object):
+    def __init__(self, **model_kwargs):
+        """ valid model_kwargs (reference monte_carlo3D.py:44-60):
+            tau_tot, imp_cnc, rho_snw, rho_ice, rsensor, hsensor, flg_crt, flg_3D, output_dir, optics_dir,
+            fi_imp, HG, phase_functions
+            additional, B200 build only: seed (int, default: OS entropy like the unseeded reference),
+            devices (list of CUDA ordinals, default: all visible), n_theta_bins (BRF tally bins, default 137)
+        """
+        model_args = self.get_model_args()
+        model_args_dict = {'tau_tot': model_args.tau_tot,
+                           'imp_cnc': model_args.imp_cnc,
+                           'rho_snw': model_args.rho_snw,
+                           'rho_ice': model_args.rho_ice,
+                           'rsensor': model_args.rsensor,
+                           'hsensor': model_args.hsensor,
+                           'flg_crt': model_args.flg_crt,
+                           'flg_3D': model_args.flg_3D,
+                           'output_dir': model_args.output_dir,
+                           'optics_dir': model_args.optics_dir,
+                           'fi_imp': model_args.fi_imp,
+                           'HG': model_args.HG,
+                           'phase_functions': model_args.phase_functions,
+                           'seed': None,
+                           'devices': None,
+                           'n_theta_bins': DEFAULT_N_THETA_BINS}
+        # kwargs given at instantiation win over config.ini / command line (monte_carlo3D.py:79-80)
+        for kwarg, val in list(model_kwargs.items()):
+            model_args_dict[kwarg] = val
+        for key, val in model_args_dict.items():
+            setattr(self, key, val)
+        self._parallel = None
+        self.last_records = None
+        self.last_tally = None
+        self.last_table = None
+        self.last_stats = None
+
+    # ---- configuration (monte_carlo3D.py:1778-1843) -----------------------------------------------------------
+    def get_model_args(self):
+        """ Specify model kwargs at run time or get values from config.ini (read from the current directory)
+        """
+        config = configparser.ConfigParser()
+        config.read('config.ini')
+
+        section_name = 'model parameters'
+        tau_tot = config.getfloat(section_name, 'tau_tot')
+        imp_cnc = config.getfloat(section_name, 'imp_cnc')
+        rho_snw = config.getfloat(section_name, 'rho_snw')
+        rho_ice = config.getfloat(section_name, 'rho_ice')
+
+        section_name = 'plot options'
+        flg_crt = config.getint(section_name, 'flg_crt')
+        flg_3D = config.getint(section_name, 'flg_3D')
+
+        section_name = 'data'
+        output_dir = config.get(section_name, 'output_dir')
+        optics_dir = config.get(section_name, 'optics_dir')
+        fi_imp = config.get(section_name, 'fi_imp')
+
+        parser = argparse.ArgumentParser(description='[DESCRIPTION]')
+        parser.add_argument('--tau_tot', type=float, default=tau_tot, help='snow optical depth')
+        parser.add_argument('--imp_cnc', type=float, default=imp_cnc,
+                            help='mass concentration of impurity [mIMP/(mIMP+mICE)]')
+        parser.add_argument('--rho_snw', type=float, default=rho_snw,
+                            help='snow density (kg/m3, only needed if flg_crt=1)')
+        parser.add_argument('--rho_ice', type=float, default=rho_ice, help='ice density (kg/m3)')
+        parser.add_argument('--rsensor', type=float, default=None, help='sensor radius [m]')
+        parser.add_argument('--hsensor', type=float, default=None, help='sensor height above snow [m]')
+        parser.add_argument('--flg_crt', type=int, default=flg_crt,
+                            help='plot in optical depth space (=0) or Cartesian space (=1)?')
+        parser.add_argument('--flg_3D', type=int, default=flg_3D,
+                            help='plot in 2-D (=0), 3-D (=1). or no plot (=999)?')
+        parser.add_argument('--output_dir', type=str, default=output_dir, help='directory to write output data')
+        parser.add_argument('--optics_dir', type=str, default=optics_dir, help='directory of optics files')
+        parser.add_argument('--fi_imp', type=str, default=fi_imp)
+        parser.add_argument('--HG', action='store_true',
+                            help='Use Henyey-Greenstein phase function instead of full scattering phase matrix '
+                                 '(this is done automatically for spherical particles)')
+        parser.add_argument('--phase_functions', action='store_true', help='Plot phase functions')
+        return parser.parse_args()
+
+    # ---- output (monte_carlo3D.py:96-143) ---------------------------------------------------------------------
+    def setup_output(self, n_photon, wvl0, half_width):
+        """ Create output dir for writing data to; returns output_file path
+        """
+        return output.setup_output(self.output_dir, wvl0, half_width, self.snow_effective_radius, n_photon,
+                                   self.theta_0)
+
+    # ---- input preparation (monte_carlo3D.py:498-777, 1553-1588) ----------------------------------------------
+    def _test_overrides(self):
+        """The reference's ``test=True`` hook: attributes preset on the instance replace table values."""
+        out = {}
+        for name in ('ssa_ice', 'ext_cff_mss_ice', 'g', 'ssa_imp', 'ext_cff_mss_imp'):
+            val = self.__dict__.get('_preset_' + name, None)
+            if val is not None:
+                out[name] = val
+        return out
+
+    def __setattr__(self, name, value):
+        # remember user presets (test_case.ssa_ice = 0.9 ...) separately: run() overwrites self.ssa_ice etc. with
+        # the per-wavelength arrays, exactly like the reference does at monte_carlo3D.py:1584-1588
+        if name in ('ssa_ice', 'ext_cff_mss_ice', 'g', 'ssa_imp', 'ext_cff_mss_imp') and np.isscalar(value):
+            self.__dict__['_preset_' + name] = value
+        object.__setattr__(self, name, value)
+
+    def build_table(self, wvl0, half_width, rds_snw, test=False):
+        """Per-wavelength SSP rows covering every wavelength the Gaussian draw can produce (ssp.py)."""
+        scale = half_width / 2.355                                  # monte_carlo3D.py:1516
+        k_lo, k_hi = ssp.wavelength_grid(wvl0, scale)
+        self.snow_effective_radius = rds_snw                        # monte_carlo3D.py:505
+        table = ssp.build_table(self.optics_dir, self.fi_imp, rds_snw, k_lo, k_hi, self.imp_cnc,
+                                overrides=self._test_overrides() if test else None,
+                                quiet=bool(test))
+        return table, k_lo, scale
+
+    # ---- the run (monte_carlo3D.py:1492-1657) -----------------------------------------------------------------
+    def run(self, n_photon, wvl0, half_width, rds_snw, theta_0=0., stokes_params=np.array([1, 0, 0, 0]),
+            shape='sphere', roughness='smooth', test=False, debug=False, Lambertian_surface=False,
+            Lambertian_bottom=True, Lambertian_reflectance=1., seed=None, write_output=True):
+        """ Run the Monte Carlo model given a normal distribution of wavelengths [um].
+            ALL VALUES IN MICRONS
+        """
+        if shape != 'sphere':
+            raise NotImplementedError('only spheres with the Henyey-Greenstein phase function are built for B200; '
+                                      'the aspherical SSP / phase-matrix files are not part of the reference '
+                                      'archive (README.md:40-42)')
+        if Lambertian_surface:
+            raise NotImplementedError('Lambertian_surface mode is not implemented in the B200 build')
+        if debug:
+            raise NotImplementedError('the two-scatter plotting demo (debug=True) is not part of the B200 build')
+        if self.phase_functions:
+            raise NotImplementedError('phase-function plotting is not part of the B200 build')
+        self.debug = debug
+        self.Lambertian_surface = Lambertian_surface
+        self.Lambertian_bottom = Lambertian_bottom
+        self.R_Lambertian = Lambertian_reflectance
+        self.theta_0 = (np.pi * theta_0) / 180.                     # theta_0 deg -> rad, monte_carlo3D.py:1508
+        self.shape = shape
+        self.roughness = roughness
+        self.wvl0 = wvl0
+        self.initial_stokes_params = stokes_params
+        n_photon = int(n_photon)
+
+        table, k_first, scale = self.build_table(wvl0, half_width, rds_snw, test=test)
+        # same attribute names as the reference, one value per table row instead of per photon
+        self.ext_cff_mss = table['ext_cff_mss']
+        self.P_ext_imp = table['p_ext_imp']
+        self.g = table['g']
+        self.ssa_ice = table['ssa_ice']
+        self.ssa_imp = table['ssa_imp']
+        self.snow_depth = ssp.snow_depth(table, self.tau_tot, self.rho_snw)     # monte_carlo3D.py:1612
+
+        if seed is None:
+            seed = self.seed
+        if seed is None:
+            seed = int.from_bytes(os.urandom(8), 'little')          # the reference never seeds np.random
+        self.last_seed = int(seed)
+
+        params = engine.make_params(self.theta_0, self.tau_tot, self.rho_snw, Lambertian_reflectance, wvl0, scale,
+                                    k_first, lambert_bottom=bool(Lambertian_bottom),
+                                    n_theta_bins=int(self.n_theta_bins))
+        par = self._parallel
+        if par is None:
+            par = self._parallel = Parallel(n_photon, devices=self.devices)
+        begin, count = par._map(n_photon)
+        ctx = par.open()
+        records, tally, stats = ctx.run(params, table, self.last_seed, begin, count, records=True, tally=True)
+        if par.size > 1:
+            ctx.reduce_tally(tally, root=0)
+        self.last_table, self.last_stats = table, stats
+
+        all_answers = par.answer_and_reduce(records, MonteCarlo.flatten_list)
+        if all_answers is None:
+            return                                                  # not the root rank
+        self.last_records, self.last_tally = all_answers, tally
+        if not write_output:
+            return
+        rows = all_answers['wvl_row'].astype(np.int64)
+        output_file = self.setup_output(n_photon, wvl0, half_width)
+        output.write_records(output_file, all_answers['condition'], (1. / table['wvl_um'])[rows],
+                             all_answers['theta_n'], all_answers['phi_n'], all_answers['n_scat'],
+                             all_answers['path_length'], self.snow_depth[rows])
+        print('%s' % output_file)   # for easy post processing
+
+    def close(self):
+        if self._parallel is not None:
+            self._parallel.close()
+            self._parallel = None
+
+    def calculate_albedo(self, answers=None):
+        """ Black sky albedo Q_up / Q_down weighted by wavenumber (monte_carlo3D.py:1659-1671), from the records of
+            the last run (or a dict of record columns)
+        """
+        answers = self.last_records if answers is None else answers
+        wvn = (1. / self.last_table['wvl_um'])[answers['wvl_row'].astype(np.int64)]
+        return wvn[answers['condition'] == 1].sum() / wvn.sum()
+
+    @classmethod
+    def flatten_list(klass, l):
+        """Concatenate per-rank record columns in rank order == photon order (monte_carlo3D.py:1845-1847)."""
+        return {k: np.concatenate([part[k] for part in l]) for k in l[0]}
+
+
+def test(n_photon=50000, wvl=0.5, half_width=0.085, rds_snw=100, **run_kwargs):
+    """ Test case for comparison with Wang et al (1995) Table 1, and van de Hulst (1980).  Albedo should be
+        ~0.09739.  Total transmittance (diffuse+direct) should be ~0.66096 (monte_carlo3D.py:1849-1866; those
+        numbers hold with the bottom boundary off: pass Lambertian_bottom=False).
+    """
+    test_case = MonteCarlo(tau_tot=2.0, imp_cnc=0)
+    test_case.ssa_ice = 0.9
+    test_case.g = 0.75
+    test_case.run(n_photon, wvl, half_width, rds_snw, test=True, **run_kwargs)
+    return test_case
+
+
+def test_and_debug(n_photon=100, wvl=0.5, half_width=0.085, rds_snw=250, **run_kwargs):
+    """ manually specified optical properties (monte_carlo3D.py:1868-1894)
+    """
+    test_case = MonteCarlo(tau_tot=10)
+    test_case.ext_cff_mss_ice = 6.6
+    test_case.ssa_ice = 0.999989859099
+    test_case.g = -0.89
+    test_case.ext_cff_mss_imp = 12000
+    test_case.ssa_imp = 0.30
+    test_case.run(n_photon, wvl, half_width, rds_snw, test=True, **run_kwargs)
+    return test_case

@@ -1,0 +1,77 @@
+"""Output file naming and writing -- byte-compatible with the reference.
+
+Reference: MonteCarlo.setup_output (monte_carloMPI/monte_carlo3D.py:96-143) and the writer block of run()
+(monte_carlo3D.py:1621-1648).  post_processing.py:24-38 parses the file name's first three '_' fields and reads
+the body with pandas.read_csv(delim_whitespace=True), so both are kept exactly:
+
+    <output_dir>/sphere/<wvl0>_<half_width>_<rds_snw>_<n_photon>_<theta0_deg>_HG[_N].txt
+    condition wvn[um^-1] theta_n phi_n n_scat path_length[m], snow_depth[m]          <- header, comma included
+    %d %r %r %r %d %r %r                                                              <- one line per photon
+
+``%r`` of a float is Python's shortest round-trip repr (the form numpy < 2 scalars print; the ``np.float64(...)``
+wrapper the unpinned reference would emit under numpy >= 2 is an environment artefact and is not imitated).
+"""
+import os
+
+import numpy as np
+
+HEADER = 'condition wvn[um^-1] theta_n phi_n n_scat path_length[m], snow_depth[m]\n'
+
+
+def theta0_deg_for_name(theta_0_rad):
+    """The reference formats np.rad2deg(self.theta_0) with self.theta_0 = pi * theta_0 / 180 (monte_carlo3D.py:1508,
+    119): the round trip is part of the file name (15 deg -> 14.999999999999998)."""
+    return np.rad2deg(theta_0_rad)
+
+
+def run_name(wvl0, half_width, rds_snw, n_photon, theta_0_rad, appendix='HG', suffix=None):
+    theta0_deg = theta0_deg_for_name(theta_0_rad)
+    if suffix is None:
+        return '%s_%s_%s_%s_%s_%s.txt' % (wvl0, half_width, rds_snw, n_photon, _plain(theta0_deg), appendix)
+    return '%s_%s_%s_%s_%s_%s_%d.txt' % (wvl0, half_width, rds_snw, n_photon, _plain(theta0_deg), appendix, suffix)
+
+
+def _plain(x):
+    """'%s' of a numpy float64 prints the bare number under every numpy version."""
+    return float(x)
+
+
+def setup_output(output_dir, wvl0, half_width, rds_snw, n_photon, theta_0_rad, shape_dir='sphere'):
+    """Create <output_dir>/<shape_dir>/ on demand and return a path that does not exist yet (``_N`` de-duplication
+    suffix, monte_carlo3D.py:135-141)."""
+    if not os.path.isdir(output_dir):
+        os.mkdir(output_dir)
+    save_dir = os.path.join(output_dir, shape_dir)
+    if not os.path.isdir(save_dir):
+        os.mkdir(save_dir)
+    path = os.path.join(save_dir, run_name(wvl0, half_width, rds_snw, n_photon, theta_0_rad))
+    i = 0
+    while os.path.isfile(path):
+        i += 1
+        path = os.path.join(save_dir, run_name(wvl0, half_width, rds_snw, n_photon, theta_0_rad, suffix=i))
+    return path
+
+
+def format_lines(condition, wvn, theta_n, phi_n, n_scat, path_length, snow_depth):
+    """Body of the output file as one string; all arguments are equal-length sequences.  Floats are widened to
+    float64 first (the reference's columns are float64), so a float32 theta prints as the double it equals."""
+    cols = (np.asarray(condition).astype(np.int64).tolist(),
+            np.asarray(wvn, dtype=np.float64).tolist(),
+            np.asarray(theta_n, dtype=np.float64).tolist(),
+            np.asarray(phi_n, dtype=np.float64).tolist(),
+            np.asarray(n_scat).astype(np.int64).tolist(),
+            np.asarray(path_length, dtype=np.float64).tolist(),
+            np.asarray(snow_depth, dtype=np.float64).tolist())
+    return ''.join(['%d %r %r %r %d %r %r\n' % row for row in zip(*cols)])
+
+
+def write_records(path, condition, wvn, theta_n, phi_n, n_scat, path_length, snow_depth, chunk=1 << 18):
+    """Write header + one line per photon, in photon order (monte_carlo3D.py:1623-1636)."""
+    n = len(condition)
+    with open(path, 'w') as f:
+        f.write(HEADER)
+        for lo in range(0, n, chunk):
+            hi = min(n, lo + chunk)
+            f.write(format_lines(condition[lo:hi], wvn[lo:hi], theta_n[lo:hi], phi_n[lo:hi], n_scat[lo:hi],
+                                 path_length[lo:hi], snow_depth[lo:hi]))
+    return path

@@ -5,10 +5,10 @@ monte_carloMPI/monte_carlo3D.py:498-658 (get_optical_properties), 661-777 (get_i
 (extinction mix, impurity probability, snow depth).  The result is the table uploaded to the GPU
 (``mc3d_ssp_row`` in include/mc3d.h): row r holds wavelength (k_first + r) / 100 um.
 
-Lookup rule of the reference, reproduced exactly (same IEEE operations as scipy's interp1d on two points):
+Lookup rule of the reference, reproduced exactly:
   * the two table rows nearest to the wavelength are selected (argsort of |wvl - wvl_in|, :2);
-  * if the wavelength lies inside their bracket: linear interpolation
-        y = ((y_hi - y_lo) / (x_hi - x_lo)) * (x - x_lo) + y_lo
+  * if the wavelength lies inside their bracket: linear interpolation between the two (np.interp, which is what
+    scipy.interpolate.interp1d(kind='linear') dispatches to for float64 data)
   * otherwise interp1d raises ValueError and the reference falls back to the nearest row's value, printing
     'error: exception raised while interpolating <name>, using nearest value instead' on stderr.
 """
@@ -30,6 +30,17 @@ def read_table(path, names):
         f.close()
 
 
+def _interp_two_points(x, y, x_new):
+    """What scipy.interpolate.interp1d(x, y)(x_new) returns for two points with x[0] < x[1], same IEEE operations:
+    native-endian float64 data go through np.interp; anything else (e.g. the big-endian arrays scipy's NetCDF
+    reader hands out, which is the case for the reference) through de Boor's two-term form
+    (scipy/interpolate/_interpolate.py, interp1d._call_linear_np / _call_linear)."""
+    native = (np.dtype(np.float64), np.dtype(int))
+    if x.dtype in native and y.dtype in native:
+        return np.interp(x_new, x, y)
+    return ((x_new - x[0]) / (x[1] - x[0])) * y[1] + ((x[1] - x_new) / (x[1] - x[0])) * y[0]
+
+
 def nearest_pair_interp(wvl_in, columns, wvls_um, warn_names=None):
     """Evaluate ``columns`` (dict name -> array over the table) at each wavelength of ``wvls_um`` [um].
 
@@ -47,8 +58,7 @@ def nearest_pair_interp(wvl_in, columns, wvls_um, warn_names=None):
         for n, col in columns.items():
             y = col[idx]
             if inside:
-                slope = (y[1] - y[0]) / (x[1] - x[0])
-                out[n][j] = slope * (wvl - x[0]) + y[0]
+                out[n][j] = _interp_two_points(x, y, wvl)
             else:
                 # ValueError path: value of the nearest row (idx_wvl[0] in the reference's ordering)
                 nearest = np.argsort(np.absolute(wvl - wvl_in))[0]

@@ -1,0 +1,69 @@
+#!/usr/bin/env python
+"""TEST INFRASTRUCTURE ONLY -- statistical golden data from the UNMODIFIED reference at 10^6 photons
+(BASELINE.json configs[1]: spheres, HG, default wavelength / grain size / zenith), for the production-mode
+3-sigma tests.  Runs K single-rank reference processes (the reference's MPI ranks are independent apart from one
+scatter and one gather) with distinct seeds and stores per-wavelength outcome counts, the 137-bin BRF zenith
+histogram of reflected photons (post_processing.py:73-76), an n_scat histogram and path-length moments.
+
+    python oracle/make_golden_stats.py [n_photon_total] [n_proc]        # ~48 core-minutes at 10^6
+"""
+import multiprocessing as mp
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+CFG = dict(wvl0=1.3, half_width=0.085, rds_snw=100., theta_0=15., tau_tot=1e6, Lambertian_bottom=True,
+           Lambertian_reflectance=0.5, fixture='spectral', n_theta_bins=137, base_seed=7000)
+
+
+def work(args):
+    rank, n, optics = args
+    from oracle import ref_shim
+    r = ref_shim.run_reference(n, CFG['wvl0'], CFG['half_width'], CFG['rds_snw'], CFG['theta_0'],
+                               seed=CFG['base_seed'] + rank, optics_dir=optics, model_kwargs=dict(tau_tot=CFG['tau_tot']),
+                               run_kwargs=dict(Lambertian_bottom=CFG['Lambertian_bottom'],
+                                               Lambertian_reflectance=CFG['Lambertian_reflectance']), record=False)
+    return {k: r[k] for k in ('condition', 'wvl', 'theta_n', 'n_scat', 'path_length')}
+
+
+def main():
+    n_total = int(float(sys.argv[1])) if len(sys.argv) > 1 else 1000000
+    n_proc = int(sys.argv[2]) if len(sys.argv) > 2 else os.cpu_count()
+    from monte_carlompi_b200 import ssp_fixtures
+    optics = os.path.join(tempfile.mkdtemp(prefix='mc3d_optics_'), 'spectral')
+    ssp_fixtures.write_optics_dir(optics, 'spectral', (100,))
+    n_chunks = n_proc * 4
+    sizes = [len(c) for c in np.array_split(np.arange(n_total), n_chunks)]
+    with mp.Pool(n_proc) as pool:
+        parts = pool.map(work, [(k, sizes[k], optics) for k in range(n_chunks)], chunksize=1)
+    cat = {k: np.concatenate([p[k] for p in parts]) for k in parts[0]}
+    k = np.rint(cat['wvl'] * 100).astype(np.int64)
+    k_lo, k_hi = int(k.min()), int(k.max())
+    nb = CFG['n_theta_bins']
+    counts = np.zeros((k_hi - k_lo + 1, 8), np.int64)
+    brf = np.zeros((k_hi - k_lo + 1, nb), np.int64)
+    for kk in range(k_lo, k_hi + 1):
+        m = k == kk
+        counts[kk - k_lo, 0] = m.sum()
+        for c in range(1, 6):
+            counts[kk - k_lo, c] = (m & (cat['condition'] == c)).sum()
+        brf[kk - k_lo] = np.histogram(cat['theta_n'][m & (cat['condition'] == 1)], bins=nb, range=(0., np.pi / 2))[0]
+    refl = cat['condition'] == 1
+    out = os.path.join(ROOT, 'tests', 'golden', 'stats_c2_reference.npz')
+    np.savez_compressed(out, config=np.array(repr(dict(CFG, n_photon=n_total))), k_first=k_lo, counts=counts, brf=brf,
+                        n_scat_hist=np.bincount(np.minimum(cat['n_scat'], 4095), minlength=4096),
+                        n_scat_sum=cat['n_scat'].sum(), path_sum=cat['path_length'].sum(),
+                        path_sq_sum=(cat['path_length'] ** 2).sum(),
+                        path_sum_reflected=cat['path_length'][refl].sum())
+    print('wrote', out, 'n', n_total, 'cond', np.bincount(cat['condition'], minlength=6)[1:], 'mean n_scat',
+          cat['n_scat'].mean())
+
+
+if __name__ == '__main__':
+    main()

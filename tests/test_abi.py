@@ -1,0 +1,61 @@
+"""The C-ABI library loads without a GPU and exports exactly what include/mc3d.h declares; the ctypes mirrors of
+its structs have the C layout.  No compute calls here."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+from monte_carlompi_b200 import engine
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, 'include', 'mc3d.h')
+
+
+def _declared():
+    src = open(HEADER).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    return sorted(set(re.findall(r'\b(mc3d_[a-z0-9_]+)\s*\(', src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = engine.load_library()
+    names = _declared()
+    assert set(names) == set(engine.EXPORTS)
+    for n in names:
+        assert getattr(lib, n) is not None
+    assert lib.mc3d_abi_version() == engine.ABI_VERSION
+
+
+def test_header_is_plain_c_and_struct_layouts_match(tmp_path):
+    prog = tmp_path / 'layout.c'
+    prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "mc3d.h"\nint main(void){'
+                    'printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(mc3d_params), sizeof(mc3d_ssp_row),'
+                    'sizeof(mc3d_records), sizeof(mc3d_records_f64), sizeof(mc3d_stats),'
+                    'offsetof(mc3d_params, k_first), offsetof(mc3d_params, n_theta_bins), offsetof(mc3d_stats, kernel_ms));'
+                    'return 0;}\n')
+    exe = tmp_path / 'layout'
+    subprocess.check_call(['gcc', '-std=c99', '-pedantic', '-Werror', '-I', os.path.join(ROOT, 'include'), str(prog), '-o', str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    want = [C.sizeof(engine.Params), engine.ROW_DTYPE.itemsize, C.sizeof(engine.Records), C.sizeof(engine.RecordsF64),
+            C.sizeof(engine.Stats), engine.Params.k_first.offset, engine.Params.n_theta_bins.offset,
+            engine.Stats.kernel_ms.offset]
+    assert got == want
+
+
+def test_no_cpu_fallback_without_a_device():
+    if engine.device_count() > 0:
+        pytest.skip('a GPU is visible')
+    with pytest.raises(engine.Mc3dError) as e:
+        engine.Context([0])
+    assert 'no CUDA device' in str(e.value)
+
+
+def test_product_package_never_touches_the_oracle():
+    pkg = os.path.join(ROOT, 'monte_carlompi_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith(('.py', '.cu', '.cuh', '.cpp', '.h')):
+                text = open(os.path.join(dirpath, fn)).read()
+                assert 'oracle' not in text.replace('oracle/mc3d_oracle.c, which is how production mode is checked', ''), fn

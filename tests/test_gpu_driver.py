@@ -1,0 +1,59 @@
+"""The drop-in driver surface end to end on a GPU: MonteCarlo().run(...) -> output file, read back the way
+post_processing.py does."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(run_dir, optics_root, kind='spectral', **kw):
+    from monte_carloMPI import monte_carlo3D
+    return monte_carlo3D.MonteCarlo(optics_dir=optics_root[kind], output_dir=str(run_dir / 'monte_carlo_results'),
+                                    devices=[0], **kw)
+
+
+def test_default_run_writes_the_reference_file(run_dir, optics_root, capsys):
+    pd = pytest.importorskip('pandas')
+    mc = _model(run_dir, optics_root, seed=20190603)
+    # the reference driver's defaults (monte_carlo3D-run.py:9-11, 18, 21, 48, 54, 84)
+    mc.run(10000, 1.3, 0.085, 100., theta_0=15., Lambertian_bottom=True, Lambertian_reflectance=0.5)
+    path = capsys.readouterr().out.strip().splitlines()[-1]                   # print(output_file), monte_carlo3D.py:1648
+    assert path == os.path.join(str(run_dir / 'monte_carlo_results'), 'sphere', '1.3_0.085_100.0_10000_14.999999999999998_HG.txt')
+    lines = open(path).read().splitlines()
+    assert lines[0] == 'condition wvn[um^-1] theta_n phi_n n_scat path_length[m], snow_depth[m]' and len(lines) == 10001
+    data = pd.read_csv(path, sep=r'\s+', float_precision='round_trip')        # post_processing.py:38
+    rec = mc.last_records
+    assert np.array_equal(data['condition'].values, rec['condition'])
+    assert np.array_equal(data['n_scat'].values, rec['n_scat'])
+    assert np.array_equal(data['theta_n'].values, rec['theta_n'].astype(np.float64))
+    wvl = np.round(1.0 / data['wvn[um^-1]'].values, 2)
+    assert abs(wvl.mean() - 1.3) < 4 * (0.085 / 2.355) / 100 and 0.03 < wvl.std() < 0.042
+    assert np.allclose(data['snow_depth[m]'].values * data['wvn[um^-1]'].values * 0 + data['snow_depth[m]'].values,
+                       1e6 / (mc.last_table['ext_cff_mss'][rec['wvl_row']] * 300.))
+    # albedo the reference's way (calculate_albedo, monte_carlo3D.py:1659-1671)
+    q_up = data[data.condition == 1]['wvn[um^-1]'].sum() / data['wvn[um^-1]'].sum()
+    assert abs(q_up - mc.calculate_albedo()) < 1e-12 and 0.35 < q_up < 0.55
+    # same seed -> same file; a second run gets the `_1` suffix (monte_carlo3D.py:135-141)
+    mc.run(10000, 1.3, 0.085, 100., theta_0=15., Lambertian_bottom=True, Lambertian_reflectance=0.5)
+    path2 = capsys.readouterr().out.strip().splitlines()[-1]
+    assert path2 == path[:-4] + '_1.txt' and open(path2).read() == open(path).read()
+    mc.close()
+
+
+def test_known_answer_through_the_driver(run_dir, optics_root):
+    from monte_carloMPI import monte_carlo3D
+    mc = monte_carlo3D.MonteCarlo(tau_tot=2.0, imp_cnc=0, optics_dir=optics_root['const-kat'], output_dir=str(run_dir / 'o'),
+                                  devices=[0], seed=3)
+    mc.ssa_ice = 0.9                          # the reference's test() (monte_carlo3D.py:1849-1866)
+    mc.g = 0.75
+    n = 2000000
+    mc.run(n, 0.5, 0.085, 100, test=True, Lambertian_bottom=False, write_output=False)
+    albedo = mc.calculate_albedo()
+    cond = mc.last_records['condition']
+    trans = ((cond == 2) | (cond == 3)).mean()
+    assert abs(albedo - 0.09739) < 3.5 * np.sqrt(0.09739 * 0.9 / n) + 2e-4
+    assert abs(trans - 0.66096) < 3.5 * np.sqrt(0.66 * 0.34 / n)
+    assert mc.last_tally[:, 0].sum() == n
+    mc.close()

@@ -1,0 +1,179 @@
+"""CPU tests of the host side: SSP lookup, output naming / writing, work partition, rendezvous, config surface."""
+import contextlib
+import io
+import multiprocessing as mp
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import golden_util as gu
+from monte_carlompi_b200 import output, parallelize, ssp
+
+
+# ---- SSP lookup: bit-identical to the arrays the reference derives (monte_carlo3D.py:498-777, 1575-1588) ------
+@pytest.mark.parametrize('name,radius,imp_cnc', [('c1_default', 100, 0.0), ('edge_of_table', 100, 0.0),
+                                                  ('impurity', 100, 1e-5), ('slab_tau3_black', 250, 0.0)])
+def test_ssp_table_matches_reference(optics_root, name, radius, imp_cnc):
+    rows = gu.load_case(name)['rows']
+    k = np.rint(rows['wvl_um'] * 100).astype(int)
+    err = io.StringIO()
+    with contextlib.redirect_stderr(err):
+        full = ssp.build_table(optics_root['spectral'], 'mie_sot_ChC90_dns_1317.nc', radius, k.min(), k.max(), imp_cnc)
+    mine = full[k - k.min()]
+    for col in rows.dtype.names:
+        assert np.array_equal(mine[col], rows[col]), col
+    # out-of-table wavelengths take the nearest row and warn like the reference (monte_carlo3D.py:536-537)
+    assert ('using nearest value instead' in err.getvalue()) == (name == 'edge_of_table')
+
+
+def test_ssp_nearest_row_outside_table(optics_root):
+    t = ssp.read_table(ssp.ice_file(optics_root['spectral'], 100), ('wvl', 'ss_alb'))
+    lo = ssp.nearest_pair_interp(t['wvl'], {'a': t['ss_alb']}, [0.30, 0.305, 0.31, 4.995, 5.0, 9.0])['a']
+    assert lo[0] == t['ss_alb'][0] and lo[1] == t['ss_alb'][0]
+    assert lo[2] == 0.5 * t['ss_alb'][0] + 0.5 * t['ss_alb'][1] or abs(lo[2] - t['ss_alb'][:2].mean()) < 1e-15
+    assert lo[3] == t['ss_alb'][-1] and lo[4] == t['ss_alb'][-1] and lo[5] == t['ss_alb'][-1]
+
+
+def test_test_hook_overrides(optics_root):
+    rows = ssp.build_table(optics_root['const-kat'], 'mie_sot_ChC90_dns_1317.nc', 100, 40, 60, 0.0,
+                           overrides={'ssa_ice': 0.9, 'g': 0.75}, quiet=True)
+    assert (rows['ssa_ice'] == 0.9).all() and (rows['g'] == 0.75).all() and (rows['p_ext_imp'] == 0).all()
+
+
+def test_wavelength_grid_covers_seven_sigma():
+    k_lo, k_hi = ssp.wavelength_grid(1.3, 0.085 / 2.355)
+    assert k_lo <= 130 - 26 and k_hi >= 130 + 26 and k_hi - k_lo < 256
+    k_lo, k_hi = ssp.wavelength_grid(1.3, 1e-15 / 2.355)          # monochromatic: a handful of rows around 1.30
+    assert k_lo <= 130 <= k_hi and k_hi - k_lo <= 4
+    assert ssp.wavelength_grid(0.05, 0.26 / 2.355)[0] == 1      # wavelengths stay positive
+
+
+# ---- output: file name and bytes (monte_carlo3D.py:96-143, 1621-1648) ------------------------------------------
+def test_output_bytes_match_reference():
+    z = np.load(os.path.join(gu.GOLDEN_DIR, 'text_default.npz'))
+    body = output.format_lines(z['condition'], z['wvn'], z['theta_n'], z['phi_n'], z['n_scat'], z['path_length'],
+                               z['snow_depth'])
+    assert output.HEADER + body == str(z['text'])
+    assert output.run_name(1.3, 0.085, 100., 40, np.pi * 15. / 180.) == str(z['name'])
+
+
+def test_run_name_theta_round_trip_quirk():
+    name = lambda deg: output.run_name(1.3, 0.085, 100., 10000, np.pi * deg / 180.)
+    assert name(15.) == '1.3_0.085_100.0_10000_14.999999999999998_HG.txt'
+    assert name(60.).split('_')[4] == '59.99999999999999'
+    assert name(0.).split('_')[4] == '0.0' and name(45.).split('_')[4] == '45.0'
+
+
+def test_setup_output_dedup_suffix(tmp_path):
+    d = str(tmp_path / 'out')
+    p0 = output.setup_output(d, 1.3, 0.085, 100., 10, 0.0)
+    open(p0, 'w').close()
+    p1 = output.setup_output(d, 1.3, 0.085, 100., 10, 0.0)
+    open(p1, 'w').close()
+    p2 = output.setup_output(d, 1.3, 0.085, 100., 10, 0.0)
+    assert os.path.dirname(p0).endswith(os.path.join('out', 'sphere'))
+    assert p1 == p0[:-4] + '_1.txt' and p2 == p0[:-4] + '_2.txt'
+
+
+def test_written_file_reads_back_like_post_processing(tmp_path):
+    pd = pytest.importorskip('pandas')
+    n = 1000
+    rng = np.random.RandomState(0)
+    cols = dict(condition=rng.randint(1, 6, n), wvn=1 / np.round(rng.normal(1.3, .04, n), 2),
+                theta_n=rng.uniform(0, np.pi, n).astype(np.float32), phi_n=rng.uniform(0, 6.28, n).astype(np.float32),
+                n_scat=rng.randint(0, 5000, n), path_length=rng.exponential(.01, n).astype(np.float32),
+                snow_depth=np.full(n, 201.8))
+    path = output.write_records(str(tmp_path / 'f.txt'), **cols)
+    data = pd.read_csv(path, sep=r'\s+', float_precision='round_trip')    # post_processing.py:38 (exact parser)
+    assert list(data.columns) == ['condition', 'wvn[um^-1]', 'theta_n', 'phi_n', 'n_scat', 'path_length[m],',
+                                  'snow_depth[m]']
+    assert np.array_equal(data['condition'].values, cols['condition'])
+    assert np.array_equal(data['theta_n'].values, cols['theta_n'].astype(np.float64))      # exact round trip
+    assert np.array_equal(data['wvn[um^-1]'].values, cols['wvn'])
+
+
+# ---- partition / ranks (parallelize.py:14-15) -----------------------------------------------------------------
+@pytest.mark.parametrize('n,parts', [(10, 3), (1000000, 8), (7, 8), (0, 4), (33, 1), (10**9, 8)])
+def test_partition_is_array_split(n, parts):
+    got = parallelize.partition(n, parts)
+    if n <= 10**6:
+        ref = np.array_split(np.arange(n), parts)
+        assert [c for _, c in got] == [len(r) for r in ref]
+        assert [b for b, c in got if c] == [int(r[0]) for r in ref if len(r)]
+    assert sum(c for _, c in got) == n and got[0][0] == 0
+    assert all(got[i][0] + got[i][1] == got[i + 1][0] for i in range(parts - 1))
+
+
+def test_detect_ranks():
+    assert parallelize.detect_ranks({}) == (0, 1, 0)
+    assert parallelize.detect_ranks({'RANK': '3', 'WORLD_SIZE': '8', 'LOCAL_RANK': '3'}) == (3, 8, 3)
+    assert parallelize.detect_ranks({'OMPI_COMM_WORLD_RANK': '1', 'OMPI_COMM_WORLD_SIZE': '2'}) == (1, 2, 1)
+
+
+def _rdzv_worker(rank, root, q):
+    r = parallelize.FileRendezvous(rank, 2, token='t', root=root, timeout=30)
+    if rank == 0:
+        r.put('nccl_id', bytes(range(128)))
+    blob = r.get('nccl_id')
+    r.barrier('b')
+    q.put((rank, blob == bytes(range(128))))
+
+
+def test_file_rendezvous_two_processes(tmp_path):
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_rdzv_worker, args=(r, str(tmp_path), q)) for r in range(2)]
+    [p.start() for p in ps]
+    got = sorted(q.get(timeout=60) for _ in ps)
+    [p.join(30) for p in ps]
+    assert got == [(0, True), (1, True)]
+
+
+def test_parallel_shape_and_gather_order():
+    par = parallelize.Parallel(10, environ={})
+    assert (par.rank, par.size, par.working_set) == (0, 1, (0, 10))
+    ans = par.answer_and_reduce({'x': np.arange(3)}, lambda parts: np.concatenate([p['x'] for p in parts]))
+    assert ans.tolist() == [0, 1, 2]
+    par2 = parallelize.Parallel(10, environ={'RANK': '1', 'WORLD_SIZE': '4', 'LOCAL_RANK': '1'})
+    assert par2.working_set == (3, 3) and par2.devices == [1]
+
+
+# ---- driver surface (monte_carlo3D.py:42-94, 1778-1843) --------------------------------------------------------
+def test_drop_in_import_path_and_config(run_dir, monkeypatch):
+    from monte_carloMPI import monte_carlo3D                      # reference monte_carlo3D-run.py:4
+    import monte_carlompi_b200.monte_carlo3D as impl
+    assert monte_carlo3D is impl
+    mc = monte_carlo3D.MonteCarlo()
+    assert (mc.tau_tot, mc.imp_cnc, mc.rho_snw, mc.rho_ice) == (1000000.0, 0.0, 300.0, 917.0)
+    assert (mc.output_dir, mc.optics_dir, mc.fi_imp) == ('monte_carlo_results', 'inputdata', 'mie_sot_ChC90_dns_1317.nc')
+    assert mc.HG is False and mc.phase_functions is False and mc.flg_3D == 999
+    monkeypatch.setattr(sys, 'argv', ['x', '--tau_tot', '10', '--optics_dir', 'elsewhere'])
+    mc = monte_carlo3D.MonteCarlo(rho_snw=200.)                   # kwargs beat flags beat config.ini
+    assert (mc.tau_tot, mc.optics_dir, mc.rho_snw) == (10.0, 'elsewhere', 200.)
+    import inspect
+    sig = inspect.signature(monte_carlo3D.MonteCarlo.run)
+    ref_args = ['self', 'n_photon', 'wvl0', 'half_width', 'rds_snw', 'theta_0', 'stokes_params', 'shape', 'roughness',
+                'test', 'debug', 'Lambertian_surface', 'Lambertian_bottom', 'Lambertian_reflectance']
+    assert list(sig.parameters)[:len(ref_args)] == ref_args      # monte_carlo3D.py:1492-1496
+    assert sig.parameters['theta_0'].default == 0. and sig.parameters['Lambertian_bottom'].default is True
+    assert sig.parameters['Lambertian_reflectance'].default == 1.
+
+
+def test_out_of_scope_modes_raise(run_dir):
+    from monte_carloMPI import monte_carlo3D
+    mc = monte_carlo3D.MonteCarlo()
+    with pytest.raises(NotImplementedError):
+        mc.run(10, 1.3, 0.085, 100., shape='droxtal')
+    with pytest.raises(NotImplementedError):
+        mc.run(10, 1.3, 0.085, 100., Lambertian_surface=True)
+
+
+def test_test_hook_presets_survive_run_attribute_overwrite(run_dir):
+    from monte_carloMPI import monte_carlo3D
+    mc = monte_carlo3D.MonteCarlo(tau_tot=2.0)
+    mc.ssa_ice = 0.9
+    mc.g = 0.75
+    mc.g = np.array([0.1, 0.2])            # what run() does with the per-wavelength arrays
+    assert mc._test_overrides() == {'ssa_ice': 0.9, 'g': 0.75}
