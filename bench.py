@@ -35,6 +35,7 @@ sys.path.insert(0, ROOT)
 WORKLOAD = dict(wvl0=1.3, half_width=0.085, rds_snw=100, theta_0=15.0, tau_tot=1e6, rho_snw=300.0,
                 lambert_bottom=True, r_lambert=0.5, n_theta_bins=137, fixture='spectral', seed=20190603)
 W_EVENT = 111.0   # algorithmic lane-instructions per scattering event
+NCU_TRAFFIC_BYTES_PER_PHOTON = 34.3   # measured once with ncu (profiles/), see roofline.traffic_is
 
 
 def build_table():
@@ -152,7 +153,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--photons', type=int, default=1000000, help='photon packets per step per GPU')
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--inflight', type=int, default=4, help='steps in flight (1..8 library slots)')
+    ap.add_argument('--inflight', type=int, default=8, help='steps in flight (1..8 library slots)')
     ap.add_argument('--launch', default='', help='blocks_per_sm,block_threads,refill_threshold (tuning)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
@@ -313,7 +314,10 @@ def main():
                                     '%s' % (stats['sm_count'], f_mhz, 'median NVML sample under load' if clocks['sm_mhz'] else 'cudaDevAttrClockRate'),
                          'achieved_is': 'events per step / (timed region / steps), %d steps in flight' % depth,
                          'isolated_launch_ms': float(np.mean(iso_ms)), 'isolated_achieved': iso, 'isolated_frac': iso / peak,
-                         'traffic': None,
+                         'traffic': NCU_TRAFFIC_BYTES_PER_PHOTON * n,
+                         'traffic_is': 'dram__bytes_read.sum + dram__bytes_write.sum of the walk kernel from the ncu --set full '
+                                       'capture at 1e6 photons per launch (profiles/r01_walk_bench_ncu_summary.csv: 34.3 MB), '
+                                       'scaled per photon; algorithmic bytes of the launch = 32 B/photon raw record',
                          'hbm': {'achieved': alg_bytes * n / (np.mean(iso_ms) * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
                                  'frac': alg_bytes * n / (np.mean(iso_ms) * 1e-3) / 1e9 / hbm_peak,
                                  'peak_is': 'hbm_gbs of MEASURED_PEAKS.json' if 'hbm_gbs' in peaks else 'fallback 6.65 TB/s'}},

@@ -179,8 +179,9 @@ int mc3d_replay(mc3d_ctx *ctx, const mc3d_params *params, uint64_t n_photon, con
                 const double *p_ext_imp, const double *init_draws, const int64_t *offsets, const double *stream,
                 const mc3d_records_f64 *out, uint64_t *n_mismatch);
 
-/* Tuning knobs (optional; defaults are chosen from the device): persistent blocks per SM, threads per block and
- * the idle-lane count at which a warp refills.  0 keeps the current value. */
+/* Tuning knobs (optional): persistent blocks per SM (default: automatic -- enough lanes for >= 26 photons each,
+ * capped by what is resident; 255 restores automatic), threads per block (128 / 256 / 512, default 256) and the
+ * number of waiting lanes at which a warp resolves / refills (default 4).  0 keeps the current value. */
 int mc3d_set_launch(mc3d_ctx *ctx, int blocks_per_sm, int block_threads, int refill_threshold);
 
 #ifdef __cplusplus

@@ -19,6 +19,7 @@
 #include <dlfcn.h>
 #include <new>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include <nccl.h>
@@ -168,7 +169,8 @@ struct mc3d_ctx {
     std::vector<Device> devs;
     std::vector<ncclComm_t> comms;   // one per device (single process) or one (multi rank)
     int rank = 0, world = 1;
-    int blocks_per_sm = 4, block_threads = 256, refill_threshold = 4;
+    int blocks_per_sm = 0;   // 0 = automatic: enough lanes for >= 26 photons each, at most the resident capacity
+    int block_threads = 256, refill_threshold = 4;
     std::chrono::steady_clock::time_point t0[N_SLOTS];
     mc3d_stats pending_stats[N_SLOTS];
 };
@@ -406,9 +408,9 @@ int mc3d_set_launch(mc3d_ctx *ctx, int blocks_per_sm, int block_threads, int ref
     if (rc) return rc;
     if (block_threads != 0 && block_threads != 128 && block_threads != 256 && block_threads != 512)
         return fail(MC3D_EINVAL, "block_threads must be 128, 256 or 512");
-    if (blocks_per_sm < 0 || blocks_per_sm > 16) return fail(MC3D_EINVAL, "blocks_per_sm out of range");
+    if (blocks_per_sm < 0 || (blocks_per_sm > 16 && blocks_per_sm != 255)) return fail(MC3D_EINVAL, "blocks_per_sm out of range");
     if (refill_threshold < 0 || refill_threshold > 32) return fail(MC3D_EINVAL, "refill_threshold must be in [1, 32]");
-    if (blocks_per_sm) ctx->blocks_per_sm = blocks_per_sm;
+    if (blocks_per_sm) ctx->blocks_per_sm = blocks_per_sm == 255 ? 0 : blocks_per_sm;
     if (block_threads) ctx->block_threads = block_threads;
     if (refill_threshold) ctx->refill_threshold = refill_threshold;
     return MC3D_OK;
@@ -483,7 +485,17 @@ int mc3d_run_async(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, const mc3d
         uint64_t off, cnt;
         array_split(n_photon, n_dev, k, &off, &cnt);
         CUDA_TRY(cudaSetDevice(d.id));
-        const int n_chunks = (int)((cnt + CHUNK_PHOTONS - 1) / CHUNK_PHOTONS);
+        // chunks of <= 2^26 photons that never cross a multiple of 2^32 in the global photon id (the walk kernel
+        // carries only the low id word per lane; the high word is a launch constant)
+        std::vector<std::pair<uint64_t, uint32_t>> chunks;   // (offset in this device's range, count)
+        for (uint64_t c_off = 0; c_off < cnt;) {
+            const uint64_t gid = photon_begin + off + c_off;
+            const uint64_t to_wrap = 0x100000000ull - (gid & 0xffffffffull);
+            const uint64_t c = std::min<uint64_t>(std::min<uint64_t>(CHUNK_PHOTONS, cnt - c_off), to_wrap);
+            chunks.emplace_back(c_off, (uint32_t)c);
+            c_off += c;
+        }
+        const int n_chunks = (int)chunks.size();
         const uint64_t chunk_cap = std::min<uint64_t>(cnt, CHUNK_PHOTONS);
 
         // ---- buffers
@@ -541,18 +553,28 @@ int mc3d_run_async(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, const mc3d
         CUDA_TRY(cudaMemsetAsync(s.tally.p, 0, (tally_len + 1) * sizeof(unsigned long long), s.stream));
 
         // ---- launch configuration: persistent grid, SM count x resident blocks
+        // Persistent grid.  A launch ends with a drain phase in which lanes that found no more photons idle while
+        // the longest walks finish; its cost grows with the number of lanes, so a launch gets only as many lanes
+        // as keep >= 26 photons per lane (at most the resident capacity, at least one block per SM).  Small
+        // launches then leave room for the next calls in flight on the other slots' streams.
+        const int bps_variant = ctx->blocks_per_sm > 0 ? ctx->blocks_per_sm : 1024 / ctx->block_threads;
         int resident = 0;
         {
             WalkParams Wq = W;
-            CUDA_TRY(launch_walk(Wq, impurity, ctx->block_threads, ctx->blocks_per_sm, 0, s.stream, &resident));
+            CUDA_TRY(launch_walk(Wq, impurity, ctx->block_threads, bps_variant, 0, s.stream, &resident));
         }
         if (resident < 1) return fail(MC3D_ECUDA, "walk kernel does not fit on an SM (block %d, rows %d)", ctx->block_threads, n_rows);
-        resident = std::min(resident, ctx->blocks_per_sm);
+        resident = std::min(resident, bps_variant);
+        if (ctx->blocks_per_sm == 0) {
+            const uint64_t want_blocks = (std::min<uint64_t>(cnt, CHUNK_PHOTONS) / 26 + ctx->block_threads - 1) / ctx->block_threads;
+            const int per_sm = (int)std::min<uint64_t>(resident, std::max<uint64_t>(1, want_blocks / d.sm_count));
+            resident = per_sm;
+        }
         st.grid_blocks = d.sm_count * resident;
 
         for (int c = 0; c < n_chunks; ++c) {
-            const uint64_t c_off = (uint64_t)c * CHUNK_PHOTONS;
-            const uint32_t c_cnt = (uint32_t)std::min<uint64_t>(CHUNK_PHOTONS, cnt - c_off);
+            const uint64_t c_off = chunks[c].first;
+            const uint32_t c_cnt = chunks[c].second;
             WalkParams Wc = W;
             Wc.photon_begin = photon_begin + off + c_off;
             Wc.n_photon = c_cnt;
@@ -562,7 +584,7 @@ int mc3d_run_async(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, const mc3d
             const int want = (int)((c_cnt + ctx->block_threads - 1) / ctx->block_threads);
             const int grid = std::max(1, std::min(st.grid_blocks, want));
             CUDA_TRY(cudaEventRecord(s.ev[2 * c], s.stream));
-            CUDA_TRY(launch_walk(Wc, impurity, ctx->block_threads, ctx->blocks_per_sm, grid, s.stream, nullptr));
+            CUDA_TRY(launch_walk(Wc, impurity, ctx->block_threads, bps_variant, grid, s.stream, nullptr));
             FinalizeParams F;
             memset(&F, 0, sizeof F);
             F.raw = s.raw.p;

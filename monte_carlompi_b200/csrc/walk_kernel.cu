@@ -7,14 +7,18 @@
 // Execution model
 //   * persistent warps; every lane walks one photon at a time.  The hot loop is one scattering event per
 //     iteration: one Philox4x32-10 block -> (HG deflection, azimuth, free path, absorption variate), rotate,
-//     move, and ONE rarely-taken branch for "left the top / hit the bottom / maybe absorbed".
-//   * a warp claims photon ids 32 at a time with a single atomicAdd (warp-aggregated by construction) and
-//     prepares them cooperatively with all 32 lanes active: wavelength draw, SSP row, and the first event
-//     (which has no deflection, monte_carlo3D.py:1232-1237).  Survivors go to a per-warp shared-memory ring;
-//     a lane whose photon terminated pops its next photon from the ring (a handful of instructions), so the
-//     divergent part of a refill is tiny and walk-length divergence is bounded by the refill threshold.
-//   * a finished photon leaves one 32-byte raw record (direction, path, n_scat, outcome); angles, records and
-//     tallies are produced by the coalesced finalize kernel (finalize_kernel.cu).
+//     move, and ONE predicate "left the top / hit the bottom / maybe absorbed / due for renormalisation".  A lane
+//     that trips it simply stops and waits.
+//   * when `refill_threshold` lanes of a warp are waiting, the warp takes one uniform branch: the waiting lanes
+//     are resolved together (the reference's termination chain in its order; finished photons store one 32-byte
+//     raw record) and the empty ones pop a fresh photon from a per-warp shared-memory ring.  The ring is filled
+//     cooperatively, 32 photon ids per atomicAdd (warp-aggregated by construction), with all 32 lanes active:
+//     wavelength draw, SSP row, and the first event (which has no deflection, monte_carlo3D.py:1232-1237).
+//     So the divergent part of a refill is a handful of shared-memory loads, and walk-length divergence is
+//     bounded by the threshold instead of by the longest walk in the warp.
+//   * when the id range is exhausted the warp drops into a drain loop that resolves lanes immediately.
+//   * angles, records and tallies are produced from the raw records by the coalesced finalize kernel
+//     (finalize_kernel.cu).
 //   * per-photon results depend only on (seed, photon id): bit-identical for any grid, block or GPU count.
 #include "mc3d_device.cuh"
 
@@ -34,15 +38,31 @@ struct Lane {
     float z, ux, uy, uz;
     float path_lo, path_hi;   // path in optical-depth units: path_hi + path_lo (flushed every 256 events)
     uint32_t i;               // events completed; 0 = the lane carries no photon
-    uint32_t pid;             // photon offset in this launch
-    uint32_t row;
-    uint32_t plo, phi;        // global photon id (Philox counter words 2, 3)
+    uint32_t plo;             // low word of the global photon id (Philox counter word 2); the high word is the
+                              // same for every photon of a launch (the host never lets a launch cross 2^32)
+    uint32_t row_addr;        // shared-space address of rows[row] (the hot loop loads the row constants through it)
     uint32_t w3;              // absorption word of the last event (for the deferred fine test)
     bool imp;                 // last event's extinction was by the impurity
-    // row constants
+};
+
+__device__ __forceinline__ uint32_t lane_row(const Lane &L, uint32_t rows_addr) { return (L.row_addr - rows_addr) / (uint32_t)sizeof(DevRow); }
+__device__ __forceinline__ uint32_t lane_pid(const WalkParams &P, const Lane &L) { return L.plo - (uint32_t)P.photon_begin; }
+
+// The part of a DevRow the hot loop needs: one 16-byte and one 4-byte shared-memory load per event (the loads are
+// issued before the Philox rounds and are off the critical path; keeping them out of registers buys occupancy).
+struct HotRow {
     float one_m_g, one_m_g2, two_g;
     uint32_t flip, t_hi;
 };
+__device__ __forceinline__ uint32_t shared_address(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ HotRow load_hot_row(uint32_t row_addr)
+{
+    HotRow h;
+    asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+        : "=f"(h.one_m_g), "=f"(h.one_m_g2), "=f"(h.two_g), "=r"(h.flip) : "r"(row_addr));
+    asm("ld.shared.u32 %0, [%1+16];" : "=r"(h.t_hi) : "r"(row_addr));
+    return h;
+}
 
 // ---- approximate special functions: one MUFU each (the XU pipe), flush-to-zero, independent of nvcc flags ----
 __device__ __forceinline__ float rcp_fast(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -89,14 +109,14 @@ constexpr uint32_t ALIVE = 0;
 
 // The scattering part of event L.i+1 given its Philox block w: HG deflection, azimuth, rotation, move.
 // monte_carlo3D.py:1252-1281 (deflection + rotation), 1352 (move), 1372 (path).  No termination logic.
-__device__ __forceinline__ void scatter_and_move(Lane &L, const uint4 w)
+__device__ __forceinline__ void scatter_and_move(Lane &L, const HotRow &H, const uint4 w)
 {
     // Henyey-Greenstein inverse CDF (790-800) in a cancellation-free form:
     //   D = 1 - g + 2 g r,  s = (1 - g^2)/D,  1 - cos = (1 - g)(1 - r)(s + 1 - g)/D,  sin^2 = (1 - cos)(1 + cos)
-    const float r = u32_to_unit(w.x ^ L.flip);
-    const float invD = rcp_fast(fmaf(L.two_g, r, L.one_m_g));
-    const float s = L.one_m_g2 * invD;
-    const float omc = (L.one_m_g * invD) * ((1.0f - r) * (s + L.one_m_g));
+    const float r = u32_to_unit(w.x ^ H.flip);
+    const float invD = rcp_fast(fmaf(H.two_g, r, H.one_m_g));
+    const float s = H.one_m_g2 * invD;
+    const float omc = (H.one_m_g * invD) * ((1.0f - r) * (s + H.one_m_g));
     const float ct = 1.0f - omc;
     const float st = sqrt_fast(omc * (2.0f - omc));
     float cp, sp;
@@ -133,9 +153,9 @@ __device__ __forceinline__ bool needs_attention(const WalkParams &P, const Lane 
 // rejection sampling about +z) so that the hot loop never carries a bottom_reflection flag.
 // Returns the condition (0 = keep walking; the lane's state is then ready for the next event).
 template <bool IMP>
-__device__ __forceinline__ uint32_t resolve(const WalkParams &P, const DevRow *rows, Lane &L)
+__device__ __forceinline__ uint32_t resolve(const WalkParams &P, const DevRow &R, Lane &L)
 {
-    const DevRow &R = rows[L.row];
+    const uint32_t phi = (uint32_t)(P.photon_begin >> 32);
     uint32_t cond = ALIVE;
     if (L.z > 0.0f) {   // reflected (1390-1397); z - z_prev = dtau muz, so the overshoot path is z / muz
         L.path_lo -= __fdividef(L.z, L.uz);
@@ -145,14 +165,14 @@ __device__ __forceinline__ uint32_t resolve(const WalkParams &P, const DevRow *r
         L.z = P.neg_tau_tot;
         cond = (L.i == 1u) ? 3u : 2u;
         if (P.lambert_bottom) {
-            const uint4 b = philox4x32_10(L.i, TAG_LAMBERT, L.plo, L.phi, P.rk);
+            const uint4 b = philox4x32_10(L.i, TAG_LAMBERT, L.plo, phi, P.rk);
             if ((long long)b.x <= P.refl_thr) {
                 // ---- reflected by the Lambertian bottom: event i+1 happens here ----
                 L.i += 1u;
-                const uint4 w = philox4x32_10(L.i, TAG_EVENT, L.plo, L.phi, P.rk);
+                const uint4 w = philox4x32_10(L.i, TAG_EVENT, L.plo, phi, P.rk);
                 float ct, st;
                 for (uint32_t j = 0;; ++j) {
-                    const uint4 a = philox4x32_10(L.i, TAG_LAMBERT | ((1u + (j >> 1)) << 8), L.plo, L.phi, P.rk);
+                    const uint4 a = philox4x32_10(L.i, TAG_LAMBERT | ((1u + (j >> 1)) << 8), L.plo, phi, P.rk);
                     const float u_t = u32_to_unit((j & 1u) ? a.z : a.x);
                     const float r1 = u32_to_unit((j & 1u) ? a.w : a.y);
                     float s_, c_;
@@ -166,7 +186,7 @@ __device__ __forceinline__ uint32_t resolve(const WalkParams &P, const DevRow *r
                 L.z = fmaf(dt2, ct, P.neg_tau_tot);
                 L.path_lo += dt2;
                 L.w3 = w.w;
-                L.imp = IMP ? species_is_impurity(P, R, L.i, L.plo, L.phi) : false;
+                L.imp = IMP ? species_is_impurity(P, R, L.i, L.plo, phi) : false;
                 cond = ALIVE;
                 if (L.z > 0.0f) {
                     L.path_lo -= __fdividef(L.z, L.uz);
@@ -179,7 +199,7 @@ __device__ __forceinline__ uint32_t resolve(const WalkParams &P, const DevRow *r
         const uint32_t t_hi = L.imp ? R.ti_hi : R.t_hi, t_lo = L.imp ? R.ti_lo : R.t_lo;
         bool absorbed = L.w3 > t_hi;
         if (L.w3 == t_hi) {   // probability 2^-32: regenerate the event's block for the low byte
-            const uint4 w = philox4x32_10(L.i, TAG_EVENT, L.plo, L.phi, P.rk);
+            const uint4 w = philox4x32_10(L.i, TAG_EVENT, L.plo, phi, P.rk);
             absorbed = (w.y & 0xffu) >= t_lo;
         }
         if (absorbed) cond = L.imp ? 5u : 4u;
@@ -193,28 +213,56 @@ __device__ __forceinline__ uint32_t resolve(const WalkParams &P, const DevRow *r
     return cond;
 }
 
-__device__ __forceinline__ void load_row_constants(Lane &L, const DevRow &R)
+// One scattering event of the photon in L (event number L.i + 1) up to and including the attention predicate.
+// Returns true while the photon simply keeps walking.
+template <bool IMP>
+__device__ __forceinline__ bool event(const WalkParams &P, const DevRow *rows, uint32_t rows_addr, Lane &L)
 {
-    L.one_m_g = R.one_m_g; L.one_m_g2 = R.one_m_g2; L.two_g = R.two_g; L.flip = R.flip; L.t_hi = R.t_hi;
+    const HotRow H = load_hot_row(L.row_addr);
+    const uint32_t phi = (uint32_t)(P.photon_begin >> 32);
+    const uint4 w = philox4x32_10(L.i + 1u, TAG_EVENT, L.plo, phi, P.rk);
+    L.i += 1u;
+    scatter_and_move(L, H, w);
+    uint32_t thi = H.t_hi;
+    if (IMP) {
+        const DevRow &R = rows[lane_row(L, rows_addr)];
+        L.imp = species_is_impurity(P, R, L.i, L.plo, phi);
+        thi = L.imp ? R.ti_hi : thi;
+    }
+    return !needs_attention(P, L, thi);
 }
 
-// Claim 32 photon ids, draw their wavelengths and take the first step (which has no deflection); append the
-// survivors to the warp's ring.  All 32 lanes execute this.  Returns 0 when the photon range is exhausted.
+// Finish (store the raw record, free the lane) or resume a lane whose last event needed attention.
 template <bool IMP>
-__device__ __forceinline__ uint32_t prepare_batch(const WalkParams &P, const DevRow *rows, WarpRing &Q,
-                                                  uint32_t &ring_tail, uint32_t lane)
+__device__ __forceinline__ bool resolve_lane(const WalkParams &P, const DevRow *rows, uint32_t rows_addr, Lane &L)
+{
+    const uint32_t row = lane_row(L, rows_addr);
+    const uint32_t cond = resolve<IMP>(P, rows[row], L);
+    if (cond == ALIVE) return true;
+    store_raw(P, lane_pid(P, L), L.ux, L.uy, L.uz, L.path_hi + L.path_lo, L.i - 1u, cond, row);
+    L.i = 0u;
+    return false;
+}
+
+constexpr uint32_t EXHAUSTED = 0xffffffffu;
+
+// Claim 32 photon ids, draw their wavelengths and take the first step (which has no deflection); append the
+// survivors to the warp's ring.  All 32 lanes execute this.  Returns the new ring tail, or EXHAUSTED when the photon
+// range has been handed out completely.
+template <bool IMP>
+__device__ __forceinline__ uint32_t prepare_batch(const WalkParams &P, const DevRow *rows, uint32_t rows_addr,
+                                                  WarpRing &Q, uint32_t ring_tail, uint32_t lane)
 {
     uint32_t base = 0;
     if (lane == 0) base = atomicAdd(P.counter, 32u);
     base = __shfl_sync(0xffffffffu, base, 0);
-    if (base >= P.n_photon) return 0u;
+    if (base >= P.n_photon) return EXHAUSTED;
     const uint32_t pid = base + lane;
     bool survive = false;
     float dtau = 0.0f;
     uint32_t row = 0;
     if (pid < P.n_photon) {
-        const unsigned long long gid = P.photon_begin + pid;
-        const uint32_t plo = (uint32_t)gid, phi = (uint32_t)(gid >> 32);
+        const uint32_t plo = (uint32_t)P.photon_begin + pid, phi = (uint32_t)(P.photon_begin >> 32);
         // wavelength: np.around(np.random.normal(wvl0, scale), 2), monte_carlo3D.py:1515-1520 (Box-Muller)
         const uint4 wv = philox4x32_10(0u, TAG_WAVELENGTH, plo, phi, P.rk);
         const float zn = sqrtf(-2.0f * logf(u32_to_unit(wv.x))) * cospif(2.0f * u32_to_unit(wv.y));
@@ -230,23 +278,17 @@ __device__ __forceinline__ uint32_t prepare_batch(const WalkParams &P, const Dev
         if (z1 < P.neg_tau_tot || w.w >= (imp ? R.ti_hi : R.t_hi)) {
             Lane L;
             L.z = z1; L.ux = P.mu0x; L.uy = 0.0f; L.uz = P.mu0z; L.i = 1u; L.path_lo = dtau; L.path_hi = 0.0f;
-            L.pid = pid; L.row = row; L.plo = plo; L.phi = phi; L.w3 = w.w; L.imp = imp;
-            load_row_constants(L, R);
-            uint32_t cond = resolve<IMP>(P, rows, L);
-            if (cond == ALIVE && L.i != 1u) {
+            L.plo = plo; L.row_addr = rows_addr + row * (uint32_t)sizeof(DevRow); L.w3 = w.w; L.imp = imp;
+            bool alive = resolve_lane<IMP>(P, rows, rows_addr, L);
+            if (alive && L.i != 1u) {
                 // reflected off the Lambertian bottom on its first step and still alive after event 2: it no
                 // longer fits the ring's "fresh photon" format, so it is walked to completion here (thin slabs only)
                 do {
-                    L.i += 1u;
-                    scatter_and_move(L, philox4x32_10(L.i, TAG_EVENT, plo, phi, P.rk));
-                    L.imp = IMP ? species_is_impurity(P, R, L.i, plo, phi) : false;
-                    if (needs_attention(P, L, L.imp ? R.ti_hi : L.t_hi)) cond = resolve<IMP>(P, rows, L);
-                } while (cond == ALIVE);
+                    alive = event<IMP>(P, rows, rows_addr, L);
+                    if (!alive) alive = resolve_lane<IMP>(P, rows, rows_addr, L);
+                } while (alive);
             }
-            if (cond != ALIVE) {
-                store_raw(P, pid, L.ux, L.uy, L.uz, L.path_hi + L.path_lo, L.i - 1u, cond, row);
-                survive = false;
-            }
+            survive = alive;
         }
     }
     const uint32_t m = __ballot_sync(0xffffffffu, survive);
@@ -256,9 +298,8 @@ __device__ __forceinline__ uint32_t prepare_batch(const WalkParams &P, const Dev
         Q.row[slot] = row;
         Q.dtau[slot] = dtau;
     }
-    ring_tail += __popc(m);
     __syncwarp();
-    return 32u;
+    return ring_tail + __popc(m);   // ring positions are free-running counters
 }
 
 template <bool IMP, int BLOCK, int MIN_BLOCKS>
@@ -272,80 +313,58 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) walk_kernel(const __grid_co
     __syncthreads();
 
     const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t rows_addr = shared_address(rows);
     WarpRing &Q = rings[threadIdx.x >> 5];
     uint32_t ring_head = 0, ring_tail = 0;   // warp-uniform
-    bool exhausted = false;                  // warp-uniform
-    uint32_t threshold = max(1u, min(32u, P.refill_threshold));
+    const uint32_t threshold = max(1u, min(32u, P.refill_threshold));
 
     Lane L;
     L.z = 0.f; L.ux = 0.f; L.uy = 0.f; L.uz = -1.f; L.path_lo = 0.f; L.path_hi = 0.f;
-    L.i = 0; L.pid = 0; L.row = 0; L.plo = 0; L.phi = 0; L.w3 = 0; L.imp = false;
-    L.one_m_g = 1.f; L.one_m_g2 = 1.f; L.two_g = 0.f; L.flip = 0; L.t_hi = 0;
-    bool alive = false;                  // false: the lane is waiting (needs attention, or carries no photon)
+    L.i = 0; L.plo = 0; L.row_addr = rows_addr; L.w3 = 0; L.imp = false;
+    bool alive = false;   // false: the lane is waiting (its last event needs attention, or it carries no photon)
 
+    // ---- phase A: steady state.  Lanes that stop just wait; when `threshold` of them are waiting the warp takes
+    // one uniform branch that resolves them together and refills the empty ones from the ring.
     for (;;) {
-        if (!__all_sync(0xffffffffu, alive)) {
-            // ------------------------------------------------------------ deferred attention + refill
-            const uint32_t waiting = __ballot_sync(0xffffffffu, !alive);
-            if (__popc(waiting) >= threshold) {
-                // 1. lanes whose last event tripped needs_attention(): finish or resume them, all together
-                if (!alive && L.i != 0u) {
-                    const uint32_t cond = resolve<IMP>(P, rows, L);
-                    if (cond != ALIVE) {
-                        store_raw(P, L.pid, L.ux, L.uy, L.uz, L.path_hi + L.path_lo, L.i - 1u, cond, L.row);
-                        L.i = 0u;
-                    } else {
-                        alive = true;
-                    }
-                }
-                // 2. lanes without a photon take a fresh one from the ring
-                const uint32_t empty = __ballot_sync(0xffffffffu, !alive);
-                const uint32_t need = __popc(empty);
-                if (need != 0u && !(exhausted && ring_head == ring_tail)) {
-                    while (!exhausted && (ring_tail - ring_head) < need)
-                        if (prepare_batch<IMP>(P, rows, Q, ring_tail, lane) == 0u) exhausted = true;
-                    const uint32_t avail = ring_tail - ring_head;
-                    if (!alive) {
-                        const uint32_t rank = __popc(empty & ((1u << lane) - 1u));
-                        if (rank < avail) {
-                            const uint32_t slot = (ring_head + rank) & (RING - 1);
-                            L.pid = Q.pid[slot];
-                            L.row = Q.row[slot];
-                            const float dtau = Q.dtau[slot];
-                            load_row_constants(L, rows[L.row]);
-                            L.ux = P.mu0x; L.uy = 0.0f; L.uz = P.mu0z;
-                            L.z = dtau * P.mu0z;
-                            L.path_lo = dtau;
-                            L.path_hi = 0.0f;
-                            L.i = 1u;
-                            const unsigned long long gid = P.photon_begin + L.pid;
-                            L.plo = (uint32_t)gid; L.phi = (uint32_t)(gid >> 32);
-                            alive = true;
-                        }
-                    }
-                    ring_head += min(avail, need);
-                    __syncwarp();
-                }
-                if (exhausted && ring_head == ring_tail) {
-                    // nothing left to hand out: from now on every waiting lane is resolved immediately
-                    threshold = 1u;
-                    if (__ballot_sync(0xffffffffu, alive) == 0u) break;
+        const uint32_t waiting = __ballot_sync(0xffffffffu, !alive);
+        if (__popc(waiting) >= threshold) {
+            if (!alive && L.i != 0u) alive = resolve_lane<IMP>(P, rows, rows_addr, L);
+            const uint32_t empty = __ballot_sync(0xffffffffu, !alive);
+            const uint32_t need = __popc(empty);
+            bool exhausted = false;
+            while ((ring_tail - ring_head) < need) {
+                const uint32_t t = prepare_batch<IMP>(P, rows, rows_addr, Q, ring_tail, lane);
+                if (t == EXHAUSTED) { exhausted = true; break; }
+                ring_tail = t;
+            }
+            const uint32_t avail = ring_tail - ring_head;
+            if (!alive) {
+                const uint32_t rank = __popc(empty & ((1u << lane) - 1u));
+                if (rank < avail) {
+                    const uint32_t slot = (ring_head + rank) & (RING - 1);
+                    const float dtau = Q.dtau[slot];
+                    L.plo = (uint32_t)P.photon_begin + Q.pid[slot];
+                    L.row_addr = rows_addr + Q.row[slot] * (uint32_t)sizeof(DevRow);
+                    L.ux = P.mu0x; L.uy = 0.0f; L.uz = P.mu0z;
+                    L.z = dtau * P.mu0z;
+                    L.path_lo = dtau;
+                    L.path_hi = 0.0f;
+                    L.i = 1u;
+                    alive = true;
                 }
             }
+            ring_head += min(avail, need);
+            __syncwarp();
+            if (exhausted) break;   // the ring is empty and no more ids exist: drain
         }
-        // ---------------------------------------------------------------- one scattering event per live lane
-        if (alive) {
-            const uint4 w = philox4x32_10(L.i + 1u, TAG_EVENT, L.plo, L.phi, P.rk);
-            L.i += 1u;
-            scatter_and_move(L, w);
-            uint32_t thi = L.t_hi;
-            if (IMP) {
-                const DevRow &R = rows[L.row];
-                L.imp = species_is_impurity(P, R, L.i, L.plo, L.phi);
-                thi = L.imp ? R.ti_hi : thi;
-            }
-            alive = !needs_attention(P, L, thi);
-        }
+        if (alive) alive = event<IMP>(P, rows, rows_addr, L);
+    }
+
+    // ---- phase B: drain.  Nothing left to hand out; every lane finishes the photon it carries.
+    for (;;) {
+        if (!alive && L.i != 0u) alive = resolve_lane<IMP>(P, rows, rows_addr, L);
+        if (__ballot_sync(0xffffffffu, alive) == 0u) break;
+        if (alive) alive = event<IMP>(P, rows, rows_addr, L);
     }
 }
 
@@ -376,7 +395,7 @@ static cudaError_t launch_variant(const WalkParams &P, bool impurity, int grid, 
 }
 
 // block_threads in {128, 256, 512}; blocks_per_sm is the occupancy target the variant is compiled for
-// (64 / 48 / 40 registers per thread for <= 32 / 40 / 48 resident warps per SM).
+// (64 / 56 / 48 / 40 registers per thread for <= 32 / 36 / 40 / 48 resident warps per SM).
 // With `occupancy` non-null nothing is launched; the resident blocks per SM are returned through it.
 cudaError_t launch_walk(const WalkParams &P, bool impurity, int block_threads, int blocks_per_sm, int grid,
                         cudaStream_t stream, int *occupancy)
@@ -384,6 +403,7 @@ cudaError_t launch_walk(const WalkParams &P, bool impurity, int block_threads, i
     const int warps_per_sm = block_threads / 32 * blocks_per_sm;
     if (block_threads == 128) {
         if (warps_per_sm <= 32) return launch_variant<128, 8>(P, impurity, grid, stream, occupancy);
+        if (warps_per_sm <= 36) return launch_variant<128, 9>(P, impurity, grid, stream, occupancy);
         if (warps_per_sm <= 40) return launch_variant<128, 10>(P, impurity, grid, stream, occupancy);
         return launch_variant<128, 12>(P, impurity, grid, stream, occupancy);
     }

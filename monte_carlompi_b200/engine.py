@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libmc3d.so')
+LIB_PATH = os.environ.get('MC3D_LIB') or os.path.join(_HERE, 'libmc3d.so')   # MC3D_LIB: A/B-test another build
 
 N_COND = 8
 N_SLOTS = 8
