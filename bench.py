@@ -308,7 +308,7 @@ def main():
                     if world == 1 else None, 'ms_per_step': 1e3 * T_e / args.steps,
                     'h2d_bytes_per_step': int(rows.nbytes + 8 * (P.n_theta_bins + 1)),
                     'd2h_bytes_per_step': int(19 * n + tallies[0].nbytes + 8), 'host_checksum': checksum},
-            'gpu_launches': 2 * args.steps * world,
+            'gpu_launches': 3 * args.steps * world,   # init + walk + finalize kernels per step and rank
             'roofline': {'bound': 'issue', 'unit': 'events/s', 'achieved': ach, 'peak': peak, 'frac': ach / peak,
                          'peak_is': 'N_SM x 128 lanes x f_SM / 111 lane-instructions per event; N_SM=%d queried, f_SM=%.0f MHz '
                                     '%s' % (stats['sm_count'], f_mhz, 'median NVML sample under load' if clocks['sm_mhz'] else 'cudaDevAttrClockRate'),

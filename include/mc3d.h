@@ -179,6 +179,18 @@ int mc3d_replay(mc3d_ctx *ctx, const mc3d_params *params, uint64_t n_photon, con
                 const double *p_ext_imp, const double *init_draws, const int64_t *offsets, const double *stream,
                 const mc3d_records_f64 *out, uint64_t *n_mismatch);
 
+/* ---- native text writer (host code; the step after the path, monte_carlo3D.py:1621-1648) ---------------------
+ * Appends one line per photon, '%d %r %r %r %d %r %r\n' % (condition, wvn, theta_n, phi_n, n_scat, path_length,
+ * snow_depth) with CPython's float repr (shortest round-trip digits), byte-identical to the reference's writer.
+ * Columns as in mc3d_records (float columns are widened to double first); wvn and snow_depth are per-row tables
+ * indexed by wvl_row.  append != 0 appends to an existing file (the caller writes the header line first).
+ * n_threads <= 0 uses every host core.  Returns the number of bytes written or a negative MC3D_E* code. */
+int64_t mc3d_write_records_text(const char *path, int append, uint64_t n, const uint8_t *condition, const int16_t *wvl_row,
+                                const float *theta_n, const float *phi_n, const uint32_t *n_scat, const float *path_length,
+                                const double *wvn_by_row, const double *snow_depth_by_row, int n_rows, int n_threads);
+/* CPython repr(x) of one double into buf (at least 32 bytes, NUL-terminated); returns its length. */
+int mc3d_py_repr(double x, char *buf);
+
 /* Tuning knobs (optional): persistent blocks per SM (default: automatic -- enough lanes for >= 26 photons each,
  * capped by what is resident; 255 restores automatic), threads per block (128 / 256 / 512, default 256) and the
  * number of waiting lanes at which a warp resolves / refills (default 4).  0 keeps the current value. */

@@ -2,7 +2,8 @@
 //
 // What the reference does around the walk and what replaces it here:
 //   Parallel._map / np.array_split + comm.scatter   (parallelize.py:14-15, 28-38)  -> photon-id ranges per device
-//   the Python photon loop                          (monte_carlo3D.py:1613-1616)   -> walk_kernel + finalize_kernel
+//   the Python photon loop                          (monte_carlo3D.py:1613-1616)   -> init_kernel + walk_kernel +
+//                                                                                      finalize_kernel
 //   comm.gather of per-photon tuples                (parallelize.py:19)            -> each device copies its id
 //                                                       range straight into the caller's SoA arrays
 //   (no reference equivalent) outcome / BRF tallies                               -> integer tallies, one
@@ -30,6 +31,7 @@
 namespace mc3d {
 cudaError_t launch_walk(const WalkParams &P, bool impurity, int block_threads, int blocks_per_sm, int grid,
                         cudaStream_t stream, int *occupancy);
+cudaError_t launch_init(const WalkParams &P, bool impurity, int sm_count, cudaStream_t stream);
 cudaError_t launch_finalize(const FinalizeParams &P, int sm_count, cudaStream_t stream);
 cudaError_t launch_replay(const ReplayParams &P, cudaStream_t stream);
 }  // namespace mc3d
@@ -135,7 +137,8 @@ struct DevBuf {
 struct Slot {
     DevBuf<DevRow> rows;
     DevBuf<double> edges;
-    DevBuf<uint32_t> counters;              // one per chunk
+    DevBuf<uint32_t> counters;              // two per chunk: walk-kernel claim counter, length of the fresh list
+    DevBuf<Fresh> fresh;                    // photons that survived their first event (init kernel -> walk kernel)
     DevBuf<RawResult> raw;
     DevBuf<uint8_t> condition;
     DevBuf<int16_t> wvl_row;
@@ -373,7 +376,7 @@ int mc3d_destroy(mc3d_ctx *ctx)
         if (cudaSetDevice(d.id) != cudaSuccess) continue;
         for (Slot &s : d.slot) {
             if (s.stream) cudaStreamSynchronize(s.stream);
-            s.rows.release(); s.edges.release(); s.counters.release(); s.raw.release(); s.condition.release();
+            s.rows.release(); s.edges.release(); s.counters.release(); s.fresh.release(); s.raw.release(); s.condition.release();
             s.wvl_row.release(); s.theta_n.release(); s.phi_n.release(); s.path_length.release();
             s.n_scat.release(); s.tally.release();
             if (s.host_tally) cudaFreeHost(s.host_tally);
@@ -501,7 +504,8 @@ int mc3d_run_async(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, const mc3d
         // ---- buffers
         CUDA_TRY(s.rows.ensure(n_rows));
         CUDA_TRY(s.edges.ensure(P->n_theta_bins + 1));
-        CUDA_TRY(s.counters.ensure(std::max(n_chunks, 1)));
+        CUDA_TRY(s.counters.ensure(2 * std::max(n_chunks, 1)));
+        CUDA_TRY(s.fresh.ensure(std::max<uint64_t>(chunk_cap, 1)));
         CUDA_TRY(s.raw.ensure(std::max<uint64_t>(chunk_cap, 1)));
         CUDA_TRY(s.tally.ensure(tally_len + 1));
         if (s.host_tally_cap < tally_len + 1) {
@@ -549,7 +553,7 @@ int mc3d_run_async(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, const mc3d
         }
         CUDA_TRY(cudaMemcpyAsync(s.rows.p, s.host_rows, n_rows * sizeof(DevRow), cudaMemcpyHostToDevice, s.stream));
         CUDA_TRY(cudaMemcpyAsync(s.edges.p, s.host_edges, (P->n_theta_bins + 1) * sizeof(double), cudaMemcpyHostToDevice, s.stream));
-        CUDA_TRY(cudaMemsetAsync(s.counters.p, 0, std::max(n_chunks, 1) * sizeof(uint32_t), s.stream));
+        CUDA_TRY(cudaMemsetAsync(s.counters.p, 0, 2 * std::max(n_chunks, 1) * sizeof(uint32_t), s.stream));
         CUDA_TRY(cudaMemsetAsync(s.tally.p, 0, (tally_len + 1) * sizeof(unsigned long long), s.stream));
 
         // ---- launch configuration: persistent grid, SM count x resident blocks
@@ -579,11 +583,14 @@ int mc3d_run_async(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, const mc3d
             Wc.photon_begin = photon_begin + off + c_off;
             Wc.n_photon = c_cnt;
             Wc.rows = s.rows.p;
-            Wc.counter = s.counters.p + c;
+            Wc.counter = s.counters.p + 2 * c;
+            Wc.n_fresh = s.counters.p + 2 * c + 1;
+            Wc.fresh = s.fresh.p;
             Wc.raw = s.raw.p;
             const int want = (int)((c_cnt + ctx->block_threads - 1) / ctx->block_threads);
             const int grid = std::max(1, std::min(st.grid_blocks, want));
             CUDA_TRY(cudaEventRecord(s.ev[2 * c], s.stream));
+            CUDA_TRY(launch_init(Wc, impurity, d.sm_count, s.stream));
             CUDA_TRY(launch_walk(Wc, impurity, ctx->block_threads, bps_variant, grid, s.stream, nullptr));
             FinalizeParams F;
             memset(&F, 0, sizeof F);

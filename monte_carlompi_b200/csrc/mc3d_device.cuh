@@ -47,6 +47,14 @@ struct __align__(16) RawResult {
     uint32_t pad0, pad1;
 };
 
+// A photon that survived its first event, waiting for a lane of the walk kernel (written by the init kernel).
+struct __align__(16) Fresh {
+    uint32_t pid;    // photon offset in this launch
+    uint32_t row;    // SSP row
+    float dtau;      // free path of the first event
+    uint32_t pad;
+};
+
 struct WalkParams {
     uint32_t rk[20];        // Philox round keys: rk[2r], rk[2r+1] for round r
     float mu0x, mu0z;       // sin(theta0), -cos(theta0)
@@ -62,7 +70,9 @@ struct WalkParams {
     uint32_t n_photon;      // photons in this launch (< 2^31)
     uint32_t pad;
     const DevRow *rows;     // [n_rows], global
-    uint32_t *counter;      // next unclaimed photon offset
+    uint32_t *counter;      // walk kernel: next unclaimed entry of `fresh`
+    uint32_t *n_fresh;      // number of entries in `fresh` (appended by the init kernel)
+    Fresh *fresh;           // [n_photon]
     RawResult *raw;         // [n_photon]
 };
 

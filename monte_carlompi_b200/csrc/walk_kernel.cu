@@ -11,296 +11,26 @@
 //     that trips it simply stops and waits.
 //   * when `refill_threshold` lanes of a warp are waiting, the warp takes one uniform branch: the waiting lanes
 //     are resolved together (the reference's termination chain in its order; finished photons store one 32-byte
-//     raw record) and the empty ones pop a fresh photon from a per-warp shared-memory ring.  The ring is filled
-//     cooperatively, 32 photon ids per atomicAdd (warp-aggregated by construction), with all 32 lanes active:
-//     wavelength draw, SSP row, and the first event (which has no deflection, monte_carlo3D.py:1232-1237).
-//     So the divergent part of a refill is a handful of shared-memory loads, and walk-length divergence is
-//     bounded by the threshold instead of by the longest walk in the warp.
+//     raw record) and the empty ones pop a fresh photon from a per-warp shared-memory ring.  The ring is refilled
+//     32 photons per atomicAdd (warp-aggregated by construction) with one coalesced 512-byte load from the
+//     `fresh` list the init kernel wrote (wavelength draw, SSP row and the deflection-free first event,
+//     monte_carlo3D.py:1232-1237, happen there).  So the divergent part of a refill is a handful of
+//     shared-memory loads, and walk-length divergence is bounded by the threshold instead of by the longest
+//     walk in the warp.  Nothing heavy is inlined next to the event loop: no spills at 48-56 registers.
 //   * when the id range is exhausted the warp drops into a drain loop that resolves lanes immediately.
 //   * angles, records and tallies are produced from the raw records by the coalesced finalize kernel
 //     (finalize_kernel.cu).
 //   * per-photon results depend only on (seed, photon id): bit-identical for any grid, block or GPU count.
-#include "mc3d_device.cuh"
+#include "walk_device.cuh"
 
 namespace mc3d {
 
 constexpr int RING = 64;  // entries per warp; a refill adds at most 32 to fewer than 32 leftovers
 
-// Fresh photons prepared by the whole warp, waiting for a lane (first event already taken).
+// Fresh photons staged for the lanes of one warp.
 struct WarpRing {
-    uint32_t pid[RING];    // photon offset in this launch
-    uint32_t row[RING];    // SSP row
-    float dtau[RING];      // free path of the first event
+    uint4 entry[RING];   // Fresh{pid, row, dtau, pad}
 };
-
-// Walk state of the photon a lane is carrying.
-struct Lane {
-    float z, ux, uy, uz;
-    float path_lo, path_hi;   // path in optical-depth units: path_hi + path_lo (flushed every 256 events)
-    uint32_t i;               // events completed; 0 = the lane carries no photon
-    uint32_t plo;             // low word of the global photon id (Philox counter word 2); the high word is the
-                              // same for every photon of a launch (the host never lets a launch cross 2^32)
-    uint32_t row_addr;        // shared-space address of rows[row] (the hot loop loads the row constants through it)
-    uint32_t w3;              // absorption word of the last event (for the deferred fine test)
-    bool imp;                 // last event's extinction was by the impurity
-};
-
-__device__ __forceinline__ uint32_t lane_row(const Lane &L, uint32_t rows_addr) { return (L.row_addr - rows_addr) / (uint32_t)sizeof(DevRow); }
-__device__ __forceinline__ uint32_t lane_pid(const WalkParams &P, const Lane &L) { return L.plo - (uint32_t)P.photon_begin; }
-
-// The part of a DevRow the hot loop needs: one 16-byte and one 4-byte shared-memory load per event (the loads are
-// issued before the Philox rounds and are off the critical path; keeping them out of registers buys occupancy).
-struct HotRow {
-    float one_m_g, one_m_g2, two_g;
-    uint32_t flip, t_hi;
-};
-__device__ __forceinline__ uint32_t shared_address(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ HotRow load_hot_row(uint32_t row_addr)
-{
-    HotRow h;
-    asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-        : "=f"(h.one_m_g), "=f"(h.one_m_g2), "=f"(h.two_g), "=r"(h.flip) : "r"(row_addr));
-    asm("ld.shared.u32 %0, [%1+16];" : "=r"(h.t_hi) : "r"(row_addr));
-    return h;
-}
-
-// ---- approximate special functions: one MUFU each (the XU pipe), flush-to-zero, independent of nvcc flags ----
-__device__ __forceinline__ float rcp_fast(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float sqrt_fast(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float rsqrt_fast(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float lg2_fast(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float sin_fast(float x) { float y; asm("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float cos_fast(float x) { float y; asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-
-constexpr float LN2 = 0.6931471805599453f;
-
-// free path -ln(u), u = (w + 0.5) 2^-32   (monte_carlo3D.py:1014, 1036)
-__device__ __forceinline__ float free_path(uint32_t w) { return -LN2 * lg2_fast(u32_to_unit(w)); }
-
-// cos, sin of the azimuth 2 pi u, u = ((w >> 8) + 0.5) 2^-24   (monte_carlo3D.py:921, 1258-1259).
-// Evaluated at 2 pi u - pi (inside the accurate range of sin/cos.approx) and negated.
-__device__ __forceinline__ void azimuth(uint32_t w, float &cp, float &sp)
-{
-    const float a = fmaf(__uint2float_rn(w >> 8), 3.7450702829239286e-07f, -3.1415922790826485f);
-    cp = -cos_fast(a);
-    sp = -sin_fast(a);
-}
-
-__device__ __forceinline__ void store_raw(const WalkParams &P, uint32_t pid, float ux, float uy, float uz,
-                                          float path, uint32_t n_scat, uint32_t cond, uint32_t row)
-{
-    RawResult *dst = P.raw + pid;
-    *reinterpret_cast<float4 *>(dst) = make_float4(ux, uy, uz, path);
-    *reinterpret_cast<uint2 *>(&dst->n_scat) = make_uint2(n_scat, cond | (row << 8));
-}
-
-// ice or impurity for event i (monte_carlo3D.py:1375-1383); only drawn when an impurity is present
-__device__ __forceinline__ bool species_is_impurity(const WalkParams &P, const DevRow &R, uint32_t i, uint32_t plo,
-                                                    uint32_t phi)
-{
-    if (!R.s_any) return false;
-    const uint4 v = philox4x32_10(i >> 2, TAG_SPECIES, plo, phi, P.rk);
-    const uint32_t sel = i & 3u;
-    const uint32_t w = sel == 0 ? v.x : sel == 1 ? v.y : sel == 2 ? v.z : v.w;
-    return w <= R.s_last;
-}
-
-constexpr uint32_t ALIVE = 0;
-
-// The scattering part of event L.i+1 given its Philox block w: HG deflection, azimuth, rotation, move.
-// monte_carlo3D.py:1252-1281 (deflection + rotation), 1352 (move), 1372 (path).  No termination logic.
-__device__ __forceinline__ void scatter_and_move(Lane &L, const HotRow &H, const uint4 w)
-{
-    // Henyey-Greenstein inverse CDF (790-800) in a cancellation-free form:
-    //   D = 1 - g + 2 g r,  s = (1 - g^2)/D,  1 - cos = (1 - g)(1 - r)(s + 1 - g)/D,  sin^2 = (1 - cos)(1 + cos)
-    const float r = u32_to_unit(w.x ^ H.flip);
-    const float invD = rcp_fast(fmaf(H.two_g, r, H.one_m_g));
-    const float s = H.one_m_g2 * invD;
-    const float omc = (H.one_m_g * invD) * ((1.0f - r) * (s + H.one_m_g));
-    const float ct = 1.0f - omc;
-    const float st = sqrt_fast(omc * (2.0f - omc));
-    float cp, sp;
-    azimuth(w.y, cp, sp);
-    const float d2 = fmaf(L.ux, L.ux, L.uy * L.uy);
-    float nx, ny, nz;
-    if (d2 < 1e-24f) {   // travelling along +-z: the reference's muz_0 == +-1 branches (1262-1269)
-        const float sg = L.uz > 0.0f ? 1.0f : -1.0f;
-        nx = st * cp; ny = sg * st * sp; nz = sg * ct;
-    } else {             // 1270-1281
-        const float a = st * rsqrt_fast(d2);
-        const float uzc = L.uz * cp;
-        nx = fmaf(a, fmaf(L.ux, uzc, -L.uy * sp), L.ux * ct);
-        ny = fmaf(a, fmaf(L.uy, uzc, L.ux * sp), L.uy * ct);
-        nz = fmaf(-(d2 * a), cp, L.uz * ct);
-    }
-    L.ux = nx; L.uy = ny; L.uz = nz;
-    const float dtau = free_path(w.z);
-    L.z = fmaf(dtau, nz, L.z);
-    L.path_lo += dtau;
-    L.w3 = w.w;
-}
-
-// "Something may have happened": the photon left the slab, may have been absorbed (coarse 32-bit test), or is
-// due for its periodic renormalisation.  Everything behind this predicate is resolved later, by resolve().
-__device__ __forceinline__ bool needs_attention(const WalkParams &P, const Lane &L, uint32_t thi)
-{
-    return L.z > 0.0f || L.z < P.neg_tau_tot || L.w3 >= thi || (L.i & 255u) == 0u;
-}
-
-// Resolve the reference's termination chain monte_carlo3D.py:1390-1466, in its order, for the event L.i that
-// just moved the photon to L.z along L.uz.  Executed by all lanes of a warp that need it at once (deferred), so it
-// is off the hot path.  On a Lambertian-bottom reflection it also performs the NEXT event (1238-1250: cosine-law
-// rejection sampling about +z) so that the hot loop never carries a bottom_reflection flag.
-// Returns the condition (0 = keep walking; the lane's state is then ready for the next event).
-template <bool IMP>
-__device__ __forceinline__ uint32_t resolve(const WalkParams &P, const DevRow &R, Lane &L)
-{
-    const uint32_t phi = (uint32_t)(P.photon_begin >> 32);
-    uint32_t cond = ALIVE;
-    if (L.z > 0.0f) {   // reflected (1390-1397); z - z_prev = dtau muz, so the overshoot path is z / muz
-        L.path_lo -= __fdividef(L.z, L.uz);
-        cond = 1u;
-    } else if (L.z < P.neg_tau_tot) {   // 1399-1459
-        L.path_lo -= __fdividef(L.z + P.tau_tot, L.uz);
-        L.z = P.neg_tau_tot;
-        cond = (L.i == 1u) ? 3u : 2u;
-        if (P.lambert_bottom) {
-            const uint4 b = philox4x32_10(L.i, TAG_LAMBERT, L.plo, phi, P.rk);
-            if ((long long)b.x <= P.refl_thr) {
-                // ---- reflected by the Lambertian bottom: event i+1 happens here ----
-                L.i += 1u;
-                const uint4 w = philox4x32_10(L.i, TAG_EVENT, L.plo, phi, P.rk);
-                float ct, st;
-                for (uint32_t j = 0;; ++j) {
-                    const uint4 a = philox4x32_10(L.i, TAG_LAMBERT | ((1u + (j >> 1)) << 8), L.plo, phi, P.rk);
-                    const float u_t = u32_to_unit((j & 1u) ? a.z : a.x);
-                    const float r1 = u32_to_unit((j & 1u) ? a.w : a.y);
-                    float s_, c_;
-                    sincosf(1.5707963267948966f * u_t, &s_, &c_);
-                    if (r1 < 2.0f * s_ * c_) { ct = c_; st = s_; break; }
-                }
-                float cp, sp;
-                azimuth(w.y, cp, sp);
-                L.ux = st * cp; L.uy = st * sp; L.uz = ct;   // muz_0 == 1 branch, 1262-1265
-                const float dt2 = free_path(w.z);
-                L.z = fmaf(dt2, ct, P.neg_tau_tot);
-                L.path_lo += dt2;
-                L.w3 = w.w;
-                L.imp = IMP ? species_is_impurity(P, R, L.i, L.plo, phi) : false;
-                cond = ALIVE;
-                if (L.z > 0.0f) {
-                    L.path_lo -= __fdividef(L.z, L.uz);
-                    cond = 1u;
-                }
-            }
-        }
-    }
-    if (cond == ALIVE) {   // 1461-1466: absorbed iff the 40-bit variate (w3 << 8 | low byte of w1) >= T40
-        const uint32_t t_hi = L.imp ? R.ti_hi : R.t_hi, t_lo = L.imp ? R.ti_lo : R.t_lo;
-        bool absorbed = L.w3 > t_hi;
-        if (L.w3 == t_hi) {   // probability 2^-32: regenerate the event's block for the low byte
-            const uint4 w = philox4x32_10(L.i, TAG_EVENT, L.plo, phi, P.rk);
-            absorbed = (w.y & 0xffu) >= t_lo;
-        }
-        if (absorbed) cond = L.imp ? 5u : 4u;
-    }
-    if (cond == ALIVE && (L.i & 255u) == 0u) {   // keyed on the photon's own event count: scheduling independent
-        const float rn = rsqrt_fast(fmaf(L.ux, L.ux, fmaf(L.uy, L.uy, L.uz * L.uz)));
-        L.ux *= rn; L.uy *= rn; L.uz *= rn;
-        L.path_hi += L.path_lo;
-        L.path_lo = 0.0f;
-    }
-    return cond;
-}
-
-// One scattering event of the photon in L (event number L.i + 1) up to and including the attention predicate.
-// Returns true while the photon simply keeps walking.
-template <bool IMP>
-__device__ __forceinline__ bool event(const WalkParams &P, const DevRow *rows, uint32_t rows_addr, Lane &L)
-{
-    const HotRow H = load_hot_row(L.row_addr);
-    const uint32_t phi = (uint32_t)(P.photon_begin >> 32);
-    const uint4 w = philox4x32_10(L.i + 1u, TAG_EVENT, L.plo, phi, P.rk);
-    L.i += 1u;
-    scatter_and_move(L, H, w);
-    uint32_t thi = H.t_hi;
-    if (IMP) {
-        const DevRow &R = rows[lane_row(L, rows_addr)];
-        L.imp = species_is_impurity(P, R, L.i, L.plo, phi);
-        thi = L.imp ? R.ti_hi : thi;
-    }
-    return !needs_attention(P, L, thi);
-}
-
-// Finish (store the raw record, free the lane) or resume a lane whose last event needed attention.
-template <bool IMP>
-__device__ __forceinline__ bool resolve_lane(const WalkParams &P, const DevRow *rows, uint32_t rows_addr, Lane &L)
-{
-    const uint32_t row = lane_row(L, rows_addr);
-    const uint32_t cond = resolve<IMP>(P, rows[row], L);
-    if (cond == ALIVE) return true;
-    store_raw(P, lane_pid(P, L), L.ux, L.uy, L.uz, L.path_hi + L.path_lo, L.i - 1u, cond, row);
-    L.i = 0u;
-    return false;
-}
-
-constexpr uint32_t EXHAUSTED = 0xffffffffu;
-
-// Claim 32 photon ids, draw their wavelengths and take the first step (which has no deflection); append the
-// survivors to the warp's ring.  All 32 lanes execute this.  Returns the new ring tail, or EXHAUSTED when the photon
-// range has been handed out completely.
-template <bool IMP>
-__device__ __forceinline__ uint32_t prepare_batch(const WalkParams &P, const DevRow *rows, uint32_t rows_addr,
-                                                  WarpRing &Q, uint32_t ring_tail, uint32_t lane)
-{
-    uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(P.counter, 32u);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (base >= P.n_photon) return EXHAUSTED;
-    const uint32_t pid = base + lane;
-    bool survive = false;
-    float dtau = 0.0f;
-    uint32_t row = 0;
-    if (pid < P.n_photon) {
-        const uint32_t plo = (uint32_t)P.photon_begin + pid, phi = (uint32_t)(P.photon_begin >> 32);
-        // wavelength: np.around(np.random.normal(wvl0, scale), 2), monte_carlo3D.py:1515-1520 (Box-Muller)
-        const uint4 wv = philox4x32_10(0u, TAG_WAVELENGTH, plo, phi, P.rk);
-        const float zn = sqrtf(-2.0f * logf(u32_to_unit(wv.x))) * cospif(2.0f * u32_to_unit(wv.y));
-        const int r = (int)rint(P.wvl0_x100 + P.sigma_x100 * (double)zn) - P.k_first;
-        row = (uint32_t)max(0, min(P.n_rows - 1, r));
-        const DevRow &R = rows[row];
-        // first event: draws of initial_pdfs (1035-1038), no deflection (1232-1237)
-        const uint4 w = philox4x32_10(1u, TAG_EVENT, plo, phi, P.rk);
-        dtau = free_path(w.z);
-        const float z1 = dtau * P.mu0z;
-        const bool imp = IMP ? species_is_impurity(P, R, 1u, plo, phi) : false;
-        survive = true;
-        if (z1 < P.neg_tau_tot || w.w >= (imp ? R.ti_hi : R.t_hi)) {
-            Lane L;
-            L.z = z1; L.ux = P.mu0x; L.uy = 0.0f; L.uz = P.mu0z; L.i = 1u; L.path_lo = dtau; L.path_hi = 0.0f;
-            L.plo = plo; L.row_addr = rows_addr + row * (uint32_t)sizeof(DevRow); L.w3 = w.w; L.imp = imp;
-            bool alive = resolve_lane<IMP>(P, rows, rows_addr, L);
-            if (alive && L.i != 1u) {
-                // reflected off the Lambertian bottom on its first step and still alive after event 2: it no
-                // longer fits the ring's "fresh photon" format, so it is walked to completion here (thin slabs only)
-                do {
-                    alive = event<IMP>(P, rows, rows_addr, L);
-                    if (!alive) alive = resolve_lane<IMP>(P, rows, rows_addr, L);
-                } while (alive);
-            }
-            survive = alive;
-        }
-    }
-    const uint32_t m = __ballot_sync(0xffffffffu, survive);
-    if (survive) {
-        const uint32_t slot = (ring_tail + __popc(m & ((1u << lane) - 1u))) & (RING - 1);
-        Q.pid[slot] = pid;
-        Q.row[slot] = row;
-        Q.dtau[slot] = dtau;
-    }
-    __syncwarp();
-    return ring_tail + __popc(m);   // ring positions are free-running counters
-}
 
 template <bool IMP, int BLOCK, int MIN_BLOCKS>
 __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) walk_kernel(const __grid_constant__ WalkParams P)
@@ -315,8 +45,9 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) walk_kernel(const __grid_co
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t rows_addr = shared_address(rows);
     WarpRing &Q = rings[threadIdx.x >> 5];
-    uint32_t ring_head = 0, ring_tail = 0;   // warp-uniform
+    uint32_t ring_head = 0, ring_tail = 0;   // warp-uniform, free-running
     const uint32_t threshold = max(1u, min(32u, P.refill_threshold));
+    const uint32_t n_fresh = *P.n_fresh;     // complete: the init kernel ran before this launch
 
     Lane L;
     L.z = 0.f; L.ux = 0.f; L.uy = 0.f; L.uz = -1.f; L.path_lo = 0.f; L.path_hi = 0.f;
@@ -333,18 +64,24 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) walk_kernel(const __grid_co
             const uint32_t need = __popc(empty);
             bool exhausted = false;
             while ((ring_tail - ring_head) < need) {
-                const uint32_t t = prepare_batch<IMP>(P, rows, rows_addr, Q, ring_tail, lane);
-                if (t == EXHAUSTED) { exhausted = true; break; }
-                ring_tail = t;
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(P.counter, 32u);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (base >= n_fresh) { exhausted = true; break; }
+                const uint32_t got = min(32u, n_fresh - base);
+                if (lane < got)
+                    Q.entry[(ring_tail + lane) & (RING - 1)] = *reinterpret_cast<const uint4 *>(P.fresh + base + lane);
+                ring_tail += got;
+                __syncwarp();
             }
             const uint32_t avail = ring_tail - ring_head;
             if (!alive) {
                 const uint32_t rank = __popc(empty & ((1u << lane) - 1u));
                 if (rank < avail) {
-                    const uint32_t slot = (ring_head + rank) & (RING - 1);
-                    const float dtau = Q.dtau[slot];
-                    L.plo = (uint32_t)P.photon_begin + Q.pid[slot];
-                    L.row_addr = rows_addr + Q.row[slot] * (uint32_t)sizeof(DevRow);
+                    const uint4 f = Q.entry[(ring_head + rank) & (RING - 1)];
+                    const float dtau = __uint_as_float(f.z);
+                    L.plo = (uint32_t)P.photon_begin + f.x;
+                    L.row_addr = rows_addr + f.y * (uint32_t)sizeof(DevRow);
                     L.ux = P.mu0x; L.uy = 0.0f; L.uz = P.mu0z;
                     L.z = dtau * P.mu0z;
                     L.path_lo = dtau;
@@ -355,7 +92,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) walk_kernel(const __grid_co
             }
             ring_head += min(avail, need);
             __syncwarp();
-            if (exhausted) break;   // the ring is empty and no more ids exist: drain
+            if (exhausted) break;   // the ring is empty and the list has been handed out: drain
         }
         if (alive) alive = event<IMP>(P, rows, rows_addr, L);
     }
@@ -395,7 +132,8 @@ static cudaError_t launch_variant(const WalkParams &P, bool impurity, int grid, 
 }
 
 // block_threads in {128, 256, 512}; blocks_per_sm is the occupancy target the variant is compiled for
-// (64 / 56 / 48 / 40 registers per thread for <= 32 / 36 / 40 / 48 resident warps per SM).
+// (56 / 53 / 48 / 40 registers per thread for <= 32 / 36 / 40 / 48 resident warps per SM; 32 warps is the default:
+// the loop is bound by the FMA pipe -- Philox's IMAD.WIDE -- and more resident warps do not raise its rate).
 // With `occupancy` non-null nothing is launched; the resident blocks per SM are returned through it.
 cudaError_t launch_walk(const WalkParams &P, bool impurity, int block_threads, int blocks_per_sm, int grid,
                         cudaStream_t stream, int *occupancy)

@@ -19,7 +19,7 @@ ABI_VERSION = 1
 
 EXPORTS = ('mc3d_abi_version', 'mc3d_last_error', 'mc3d_query', 'mc3d_create', 'mc3d_nccl_unique_id',
            'mc3d_create_rank', 'mc3d_destroy', 'mc3d_host_alloc', 'mc3d_host_free', 'mc3d_run', 'mc3d_run_async',
-           'mc3d_wait', 'mc3d_reduce_tally', 'mc3d_replay', 'mc3d_set_launch')
+           'mc3d_wait', 'mc3d_reduce_tally', 'mc3d_replay', 'mc3d_set_launch', 'mc3d_write_records_text', 'mc3d_py_repr')
 
 
 class Mc3dError(RuntimeError):
@@ -88,6 +88,9 @@ def load_library():
     lib.mc3d_reduce_tally.argtypes = [vp, vp, u64, i32]
     lib.mc3d_replay.argtypes = [vp, vp, u64] + [vp] * 11
     lib.mc3d_set_launch.argtypes = [vp, i32, i32, i32]
+    lib.mc3d_write_records_text.restype = C.c_int64
+    lib.mc3d_write_records_text.argtypes = [C.c_char_p, i32, u64, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32]
+    lib.mc3d_py_repr.argtypes = [C.c_double, C.c_char_p]
     if lib.mc3d_abi_version() != ABI_VERSION:
         raise Mc3dError('libmc3d.so ABI %d != expected %d' % (lib.mc3d_abi_version(), ABI_VERSION))
     _lib = lib
@@ -131,6 +134,28 @@ def make_params(theta0_rad, tau_tot, rho_snw, r_lambert, wvl0_um, sigma_um, k_fi
     flags = (FLAG_LAMBERT_BOTTOM if lambert_bottom else 0) | (FLAG_LAMBERT_SURFACE if lambert_surface else 0)
     return Params(float(theta0_rad), float(tau_tot), float(rho_snw), float(r_lambert), float(wvl0_um),
                   float(sigma_um), int(k_first), flags, int(n_theta_bins), 0)
+
+
+def py_repr(x):
+    """CPython's repr(float) computed by the native formatter (for tests)."""
+    buf = C.create_string_buffer(40)
+    n = load_library().mc3d_py_repr(float(x), buf)
+    return buf.raw[:n].decode('ascii')
+
+
+def write_records_text(path, records, wvn_by_row, snow_depth_by_row, append=True, n_threads=0):
+    """Append the reference's '%d %r %r %r %d %r %r' lines for a dict of record columns (native, multithreaded)."""
+    cols = {name: np.ascontiguousarray(records[name], dtype=dt) for name, dt in RECORD_COLUMNS}
+    wvn = np.ascontiguousarray(wvn_by_row, dtype=np.float64)
+    depth = np.ascontiguousarray(snow_depth_by_row, dtype=np.float64)
+    n = len(cols['condition'])
+    rc = load_library().mc3d_write_records_text(os.fsencode(path), 1 if append else 0, n, _ptr(cols['condition']),
+                                                _ptr(cols['wvl_row']), _ptr(cols['theta_n']), _ptr(cols['phi_n']),
+                                                _ptr(cols['n_scat']), _ptr(cols['path_length']), _ptr(wvn), _ptr(depth),
+                                                len(wvn), int(n_threads))
+    if rc < 0:
+        raise Mc3dError('mc3d_write_records_text failed with %d for %s' % (rc, path))
+    return int(rc)
 
 
 class PinnedArray(object):

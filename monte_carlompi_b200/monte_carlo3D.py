@@ -205,11 +205,8 @@ class MonteCarlo(object):
         self.last_records, self.last_tally = all_answers, tally
         if not write_output:
             return
-        rows = all_answers['wvl_row'].astype(np.int64)
         output_file = self.setup_output(n_photon, wvl0, half_width)
-        output.write_records(output_file, all_answers['condition'], (1. / table['wvl_um'])[rows],
-                             all_answers['theta_n'], all_answers['phi_n'], all_answers['n_scat'],
-                             all_answers['path_length'], self.snow_depth[rows])
+        output.write_run(output_file, all_answers, 1. / table['wvl_um'], self.snow_depth)
         print('%s' % output_file)   # for easy post processing
 
     def close(self):

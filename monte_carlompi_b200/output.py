@@ -65,6 +65,17 @@ def format_lines(condition, wvn, theta_n, phi_n, n_scat, path_length, snow_depth
     return ''.join(['%d %r %r %r %d %r %r\n' % row for row in zip(*cols)])
 
 
+def write_run(path, records, wvn_by_row, snow_depth_by_row):
+    """Header + one line per photon from the compact record columns of libmc3d (``wvl_row`` indexes the per-row
+    ``wvn`` / ``snow_depth`` tables).  Lines are formatted by the native multithreaded writer
+    (csrc/format_records.cpp), byte-identical to ``format_lines`` and ~20x faster."""
+    from . import engine
+    with open(path, 'w') as f:
+        f.write(HEADER)
+    engine.write_records_text(path, records, wvn_by_row, snow_depth_by_row, append=True)
+    return path
+
+
 def write_records(path, condition, wvn, theta_n, phi_n, n_scat, path_length, snow_depth, chunk=1 << 18):
     """Write header + one line per photon, in photon order (monte_carlo3D.py:1623-1636)."""
     n = len(condition)

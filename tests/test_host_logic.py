@@ -59,6 +59,30 @@ def test_output_bytes_match_reference():
     assert output.run_name(1.3, 0.085, 100., 40, np.pi * 15. / 180.) == str(z['name'])
 
 
+def test_native_writer_is_byte_identical_to_python_repr(tmp_path):
+    from monte_carlompi_b200 import engine
+    rng = np.random.RandomState(1)
+    vals = np.concatenate([rng.uniform(0, 7, 5000), 10.0 ** rng.uniform(-12, 20, 5000),
+                           rng.standard_normal(2000).astype(np.float32).astype(np.float64),
+                           [0.0, -0.0, 1.0, 1e16, 1e-4, 9.999e-5, 123456789012345680.0, 1e22, 5e-324, 1.7976931348623157e308,
+                            0.1, 100.0, 1e15, 9999999999999998.0, 1e-5, 0.7692307692307693, float('inf'), -float('inf')]])
+    for v in vals:
+        assert engine.py_repr(v) == repr(float(v)), v
+    assert engine.py_repr(float('nan')) == 'nan'
+    n = 70001                                   # more than one 65536-line work item, ragged tail
+    rec = dict(condition=rng.randint(1, 6, n).astype(np.uint8), wvl_row=rng.randint(0, 53, n).astype(np.int16),
+               theta_n=rng.uniform(0, np.pi, n).astype(np.float32), phi_n=rng.uniform(0, 6.28, n).astype(np.float32),
+               n_scat=rng.randint(0, 500000, n).astype(np.uint32), path_length=rng.exponential(.01, n).astype(np.float32))
+    rec['phi_n'][::7] = 0.0                     # unscattered photons print 0.0
+    wvn, depth = 1 / np.round(rng.uniform(1.0, 1.6, 53), 2), rng.uniform(100, 300, 53)
+    path = output.write_run(str(tmp_path / 'native.txt'), rec, wvn, depth)
+    want = output.HEADER + output.format_lines(rec['condition'], wvn[rec['wvl_row']], rec['theta_n'], rec['phi_n'],
+                                               rec['n_scat'], rec['path_length'], depth[rec['wvl_row']])
+    assert open(path).read() == want
+    z = np.load(os.path.join(gu.GOLDEN_DIR, 'text_default.npz'))   # and against the reference's own bytes
+    assert engine.py_repr(float(z['theta_n'][3])) in str(z['text'])
+
+
 def test_run_name_theta_round_trip_quirk():
     name = lambda deg: output.run_name(1.3, 0.085, 100., 10000, np.pi * deg / 180.)
     assert name(15.) == '1.3_0.085_100.0_10000_14.999999999999998_HG.txt'
@@ -177,3 +201,27 @@ def test_test_hook_presets_survive_run_attribute_overwrite(run_dir):
     mc.g = 0.75
     mc.g = np.array([0.1, 0.2])            # what run() does with the per-wavelength arrays
     assert mc._test_overrides() == {'ssa_ice': 0.9, 'g': 0.75}
+
+
+# ---- BRF / albedo from tallies == the reference's per-photon formulas (post_processing.py:73-81) ---------------
+def test_brf_and_albedo_from_tallies_match_per_photon_formulas():
+    import gpu_util_cpu as gc
+    from monte_carlompi_b200 import engine, post
+    assert post.calculate_bins() == 137 and post.calculate_bins(2., 175.) == 68
+    rng = np.random.RandomState(5)
+    n, n_rows, nb = 200000, 7, 137
+    table = np.zeros(n_rows, engine.ROW_DTYPE)
+    table['wvl_um'] = 1.27 + 0.01 * np.arange(n_rows)
+    rec = dict(wvl_row=rng.randint(0, n_rows, n).astype(np.int16), condition=rng.choice([1, 2, 3, 4, 5], n, p=[.4, .1, .05, .4, .05]).astype(np.uint8),
+               theta_n=np.arccos(np.sqrt(rng.uniform(0, 1, n))).astype(np.float32))
+    tally = gc.tally_from_records(rec, n_rows, nb)
+    wvn = (1. / table['wvl_um'])[rec['wvl_row']]
+    mid_t, brf_t = post.brf_from_tally(tally, table)
+    mid_r, brf_r = post.brf_from_records(rec['condition'], wvn, rec['theta_n'], nb)
+    assert np.array_equal(mid_t, mid_r) and np.allclose(brf_t, brf_r, rtol=1e-12, atol=0)
+    q_up = wvn[rec['condition'] == 1].sum() / wvn.sum()
+    assert abs(post.albedo_from_tally(tally, table) - q_up) < 1e-13
+    fr = post.outcome_fractions(tally)
+    assert abs(fr[1] - (rec['condition'] == 1).mean()) < 1e-15 and abs(sum(fr.values()) - 1) < 1e-12
+    # a Lambertian reflector has BRF == albedo in every bin (cos-law sampling above): check the normalisation
+    assert abs(np.median(brf_t) - q_up) < 0.02
