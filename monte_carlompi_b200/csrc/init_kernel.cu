@@ -48,6 +48,7 @@ __global__ void __launch_bounds__(BLOCK) init_kernel(const __grid_constant__ Wal
                 Lane L;
                 L.z = z1; L.ux = P.mu0x; L.uy = 0.0f; L.uz = P.mu0z; L.i = 1u; L.path_lo = dtau; L.path_hi = 0.0f;
                 L.plo = plo; L.row_addr = rows_addr + row * (uint32_t)sizeof(DevRow); L.w3 = w.w; L.imp = imp;
+                L.pk = philox_event_constants(plo, P.rk);
                 bool alive = resolve_lane<IMP>(P, rows, rows_addr, L);
                 if (alive && L.i != 1u) {
                     // reflected off the Lambertian bottom on its first step and still alive after event 2: it no

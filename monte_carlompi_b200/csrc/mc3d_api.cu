@@ -206,7 +206,8 @@ static bool build_rows(const mc3d_params *P, const mc3d_ssp_row *table, int n_ro
         DevRow &d = out[r];
         d.one_m_g = (float)(1.0 - s.g);
         d.one_m_g2 = (float)(1.0 - s.g * s.g);
-        d.two_g = (float)(2.0 * s.g);
+        d.d_scale = (float)std::ldexp(2.0 * s.g, -32);
+        d.d_off = (float)(1.0 - s.g + std::ldexp(s.g, -32));
         d.flip = (s.g == 0.0) ? 0xffffffffu : 0u;
         threshold40(s.ssa_ice, &d.t_hi, &d.t_lo);
         threshold40(s.ssa_imp, &d.ti_hi, &d.ti_lo);
@@ -220,8 +221,7 @@ static bool build_rows(const mc3d_params *P, const mc3d_ssp_row *table, int n_ro
             d.s_any = 0u;
             d.s_last = 0u;
         }
-        d.inv_ext = (float)(1.0 / (s.ext_cff_mss * P->rho_snw));
-        d.pad = 0.0f;
+        d.inv_ext = (float)(0.6931471805599453 / (s.ext_cff_mss * P->rho_snw));
     }
     return impurity;
 }
@@ -461,7 +461,7 @@ int mc3d_run_async(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, const mc3d
     philox_round_keys(seed, W.rk);
     W.mu0x = (float)std::sin(P->theta0_rad);
     W.mu0z = (float)(-std::cos(P->theta0_rad));
-    W.tau_tot = (float)P->tau_tot;
+    W.tau_tot = (float)(P->tau_tot / 0.6931471805599453);   // the walk's depth unit is ln 2 optical depths
     W.neg_tau_tot = -W.tau_tot;
     W.wvl0_x100 = P->wvl0_um * 100.0;
     W.sigma_x100 = P->sigma_um * 100.0;

@@ -24,24 +24,27 @@ constexpr int N_COND = 8;
 
 // Per-wavelength row in the form the walk consumes (built on the host from mc3d_ssp_row, fp64 -> fp32/integer).
 struct DevRow {
+    // -- first 24 bytes: what the event loop loads (one 16-byte + one 8-byte shared-memory load)
     float one_m_g;    // 1 - g
     float one_m_g2;   // 1 - g^2
-    float two_g;      // 2 g
+    float d_scale;    // 2 g 2^-32:      D = 1 - g + 2 g r = fma(float(w), d_scale, d_off), r = (w + 1/2) 2^-32
     uint32_t flip;    // 0xffffffff when g == 0 (maps the factored HG form onto the reference's 1 - 2r branch)
     uint32_t t_hi;    // ice: absorbed iff K40 >= T40 = ceil(ssa 2^40 - 1/2); t_hi = T40 >> 8 (saturated)
+    float d_off;      // 1 - g + g 2^-32
+    // -- resolve / finalize only
     uint32_t t_lo;    //      t_lo = T40 & 0xff, or 256 when T40 == 2^40 (never absorbed)
     uint32_t ti_hi;   // same for the impurity's single-scatter albedo
     uint32_t ti_lo;
     uint32_t s_last;  // impurity iff species word <= s_last (and s_any)
     uint32_t s_any;   // 0 when P_ext_imp == 0 (species word never selects the impurity)
-    float inv_ext;    // 1 / (ext_cff_mss rho_snw): metres per unit optical depth
-    float pad;
+    float inv_ext;    // ln 2 / (ext_cff_mss rho_snw): metres per unit of the walk's depth scale (optical depth / ln 2)
 };
+static_assert(sizeof(DevRow) == 48, "DevRow is 48 bytes");
 
 // Raw result of one walk (32 B, one sector, written by the lane that finished the photon).
 struct __align__(16) RawResult {
     float ux, uy, uz;   // final direction cosines
-    float path_tau;     // path inside the slab in optical-depth units
+    float path_tau;     // path inside the slab in units of ln 2 optical depths (DevRow::inv_ext converts to metres)
     uint32_t n_scat;    // i - 1
     uint32_t meta;      // condition | row << 8
     uint32_t pad0, pad1;
@@ -58,8 +61,8 @@ struct __align__(16) Fresh {
 struct WalkParams {
     uint32_t rk[20];        // Philox round keys: rk[2r], rk[2r+1] for round r
     float mu0x, mu0z;       // sin(theta0), -cos(theta0)
-    float neg_tau_tot;      // -tau_tot
-    float tau_tot;
+    float neg_tau_tot;      // -tau_tot / ln 2: depths and paths are carried in units of ln 2 optical depths, so that
+    float tau_tot;          //  tau_tot / ln 2   a free path is just -log2(u) (no multiply by ln 2 per event)
     double wvl0_x100, sigma_x100;  // wavelength draw in units of 0.01 um
     int32_t k_first;
     int32_t n_rows;
@@ -126,6 +129,37 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
 {
 #pragma unroll
     for (int r = 0; r < 10; ++r) philox_round(c0, c1, c2, c3, rk[2 * r], rk[2 * r + 1]);
+    return make_uint4(c0, c1, c2, c3);
+}
+
+// Event block (tag TAG_EVENT = 0) with the photon-constant part of rounds 1 and 2 hoisted out of the walk:
+//   round 1 multiplies M1 by counter word 2 = pid_lo, round 2 multiplies M0 by the round-1 word 0, which depends on
+//   pid only.  pB = lo(M1 pid_lo), (pC, pD) = mulhilo(M0, hi(M1 pid_lo) ^ TAG_EVENT ^ rk[0]) are computed once per
+//   photon (philox_event_constants); 18 instead of 20 wide multiplies per event, identical output.
+struct PhiloxEventConst { uint32_t pB, pC, pD; };
+
+__device__ __forceinline__ PhiloxEventConst philox_event_constants(uint32_t plo, const uint32_t *__restrict__ rk)
+{
+    PhiloxEventConst k;
+    const uint32_t a = __umulhi(PHILOX_M1, plo) ^ TAG_EVENT ^ rk[0];
+    k.pB = PHILOX_M1 * plo;
+    k.pC = __umulhi(PHILOX_M0, a);
+    k.pD = PHILOX_M0 * a;
+    return k;
+}
+
+__device__ __forceinline__ uint4 philox_event(uint32_t i, uint32_t phi, const PhiloxEventConst k, const uint32_t *__restrict__ rk)
+{
+    // round 1: (c0, c1, c2, c3) = (i, TAG_EVENT, plo, phi)
+    uint32_t c2 = __umulhi(PHILOX_M0, i) ^ phi ^ rk[1];
+    uint32_t c3 = PHILOX_M0 * i;
+    // round 2: word 0 of round 1 is photon-constant, its products are pC (hi) and pD (lo)
+    uint32_t c0 = __umulhi(PHILOX_M1, c2) ^ k.pB ^ rk[2];
+    uint32_t c1 = PHILOX_M1 * c2;
+    c2 = k.pC ^ c3 ^ rk[3];
+    c3 = k.pD;
+#pragma unroll
+    for (int r = 2; r < 10; ++r) philox_round(c0, c1, c2, c3, rk[2 * r], rk[2 * r + 1]);
     return make_uint4(c0, c1, c2, c3);
 }
 

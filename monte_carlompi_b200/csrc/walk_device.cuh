@@ -16,6 +16,7 @@ struct Lane {
                               // same for every photon of a launch (the host never lets a launch cross 2^32)
     uint32_t row_addr;        // shared-space address of rows[row] (the hot loop loads the row constants through it)
     uint32_t w3;              // absorption word of the last event (for the deferred fine test)
+    PhiloxEventConst pk;      // photon-constant part of the event block's first two Philox rounds
     bool imp;                 // last event's extinction was by the impurity
 };
 
@@ -25,7 +26,7 @@ __device__ __forceinline__ uint32_t lane_pid(const WalkParams &P, const Lane &L)
 // The part of a DevRow the hot loop needs: one 16-byte and one 4-byte shared-memory load per event (the loads are
 // issued before the Philox rounds and are off the critical path; keeping them out of registers buys occupancy).
 struct HotRow {
-    float one_m_g, one_m_g2, two_g;
+    float one_m_g, one_m_g2, d_scale, d_off;
     uint32_t flip, t_hi;
 };
 __device__ __forceinline__ uint32_t shared_address(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -33,8 +34,8 @@ __device__ __forceinline__ HotRow load_hot_row(uint32_t row_addr)
 {
     HotRow h;
     asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-        : "=f"(h.one_m_g), "=f"(h.one_m_g2), "=f"(h.two_g), "=r"(h.flip) : "r"(row_addr));
-    asm("ld.shared.u32 %0, [%1+16];" : "=r"(h.t_hi) : "r"(row_addr));
+        : "=f"(h.one_m_g), "=f"(h.one_m_g2), "=f"(h.d_scale), "=r"(h.flip) : "r"(row_addr));
+    asm("ld.shared.v2.u32 {%0, %1}, [%2+16];" : "=r"(h.t_hi), "=f"(h.d_off) : "r"(row_addr));
     return h;
 }
 
@@ -48,8 +49,8 @@ __device__ __forceinline__ float cos_fast(float x) { float y; asm("cos.approx.ft
 
 constexpr float LN2 = 0.6931471805599453f;
 
-// free path -ln(u), u = (w + 0.5) 2^-32   (monte_carlo3D.py:1014, 1036)
-__device__ __forceinline__ float free_path(uint32_t w) { return -LN2 * lg2_fast(u32_to_unit(w)); }
+// free path -ln(u) / ln 2 = -log2(u), u = (w + 0.5) 2^-32   (monte_carlo3D.py:1014, 1036), in the walk's depth unit
+__device__ __forceinline__ float free_path(uint32_t w) { return -lg2_fast(u32_to_unit(w)); }
 
 // cos, sin of the azimuth 2 pi u, u = ((w >> 8) + 0.5) 2^-24   (monte_carlo3D.py:921, 1258-1259).
 // Evaluated at 2 pi u - pi (inside the accurate range of sin/cos.approx) and negated.
@@ -87,10 +88,11 @@ __device__ __forceinline__ void scatter_and_move(Lane &L, const HotRow &H, const
 {
     // Henyey-Greenstein inverse CDF (790-800) in a cancellation-free form:
     //   D = 1 - g + 2 g r,  s = (1 - g^2)/D,  1 - cos = (1 - g)(1 - r)(s + 1 - g)/D,  sin^2 = (1 - cos)(1 + cos)
-    const float r = u32_to_unit(w.x ^ H.flip);
-    const float invD = rcp_fast(fmaf(H.two_g, r, H.one_m_g));
+    const float wf = __uint2float_rn(w.x ^ H.flip);
+    const float invD = rcp_fast(fmaf(wf, H.d_scale, H.d_off));          // D = 1 - g + 2 g r
+    const float omr = fmaf(wf, -2.3283064365386963e-10f, 1.0f);         // 1 - r
     const float s = H.one_m_g2 * invD;
-    const float omc = (H.one_m_g * invD) * ((1.0f - r) * (s + H.one_m_g));
+    const float omc = (H.one_m_g * invD) * (omr * (s + H.one_m_g));
     const float ct = 1.0f - omc;
     const float st = sqrt_fast(omc * (2.0f - omc));
     float cp, sp;
@@ -194,7 +196,7 @@ __device__ __forceinline__ bool event(const WalkParams &P, const DevRow *rows, u
 {
     const HotRow H = load_hot_row(L.row_addr);
     const uint32_t phi = (uint32_t)(P.photon_begin >> 32);
-    const uint4 w = philox4x32_10(L.i + 1u, TAG_EVENT, L.plo, phi, P.rk);
+    const uint4 w = philox_event(L.i + 1u, phi, L.pk, P.rk);   // == philox4x32_10(i + 1, TAG_EVENT, plo, phi)
     L.i += 1u;
     scatter_and_move(L, H, w);
     uint32_t thi = H.t_hi;

@@ -52,6 +52,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) walk_kernel(const __grid_co
     Lane L;
     L.z = 0.f; L.ux = 0.f; L.uy = 0.f; L.uz = -1.f; L.path_lo = 0.f; L.path_hi = 0.f;
     L.i = 0; L.plo = 0; L.row_addr = rows_addr; L.w3 = 0; L.imp = false;
+    L.pk.pB = L.pk.pC = L.pk.pD = 0;
     bool alive = false;   // false: the lane is waiting (its last event needs attention, or it carries no photon)
 
     // ---- phase A: steady state.  Lanes that stop just wait; when `threshold` of them are waiting the warp takes
@@ -81,6 +82,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) walk_kernel(const __grid_co
                     const uint4 f = Q.entry[(ring_head + rank) & (RING - 1)];
                     const float dtau = __uint_as_float(f.z);
                     L.plo = (uint32_t)P.photon_begin + f.x;
+                    L.pk = philox_event_constants(L.plo, P.rk);
                     L.row_addr = rows_addr + f.y * (uint32_t)sizeof(DevRow);
                     L.ux = P.mu0x; L.uy = 0.0f; L.uz = P.mu0z;
                     L.z = dtau * P.mu0z;
