@@ -429,8 +429,6 @@ static int validate_run(const mc3d_params *P, const mc3d_ssp_row *table, int n_r
     if (!(P->theta0_rad >= 0.0 && P->theta0_rad < 1.5707963267948966))
         return fail(MC3D_EINVAL, "theta0 must be in [0, pi/2)");
     if (!(P->sigma_um >= 0.0)) return fail(MC3D_EINVAL, "sigma must be >= 0");
-    if (P->flags & MC3D_FLAG_LAMBERT_SURFACE)
-        return fail(MC3D_EINVAL, "Lambertian_surface mode is not implemented in production mode (use replay)");
     for (int r = 0; r < n_rows; ++r) {
         if (!(table[r].ext_cff_mss > 0.0)) return fail(MC3D_EINVAL, "row %d: ext_cff_mss must be positive", r);
         if (!(table[r].g > -1.0 && table[r].g < 1.0)) return fail(MC3D_EINVAL, "row %d: g must be in (-1, 1)", r);
@@ -472,6 +470,8 @@ int mc3d_run_async(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, const mc3d
         W.refl_thr = t < -1.0 ? -1 : (t > 4294967295.0 ? 4294967295ll : (long long)t);
     }
     W.lambert_bottom = (P->flags & MC3D_FLAG_LAMBERT_BOTTOM) ? 1u : 0u;
+    W.lambert_surface = (P->flags & MC3D_FLAG_LAMBERT_SURFACE) ? 1u : 0u;
+    threshold40(P->r_lambert, &W.surf_t_hi, &W.surf_t_lo);
     W.refill_threshold = (uint32_t)ctx->refill_threshold;
 
     mc3d_stats &st = ctx->pending_stats[slot_idx];

@@ -69,6 +69,9 @@ struct WalkParams {
     int64_t refl_thr;       // bottom reflects iff (int64)w <= refl_thr  (U(w) <= R)
     uint32_t lambert_bottom;
     uint32_t refill_threshold;
+    uint32_t lambert_surface;   // run(Lambertian_surface=True): the init kernel finishes every photon by itself
+    uint32_t surf_t_hi, surf_t_lo;   // 40-bit threshold of the surface reflectance (ssa_event = R, monte_carlo3D.py:1385-1387)
+    uint32_t pad2;
     uint64_t photon_begin;  // global id of photon 0 of this launch
     uint32_t n_photon;      // photons in this launch (< 2^31)
     uint32_t pad;

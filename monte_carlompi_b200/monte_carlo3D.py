@@ -11,7 +11,7 @@ binding).  Wavelengths are drawn on the GPU from a Philox4x32-10 stream keyed on
 per-photon SSP arrays of the reference become one small per-wavelength table (ssp.py).
 
 Not carried over (out of scope): aspherical grain shapes / full phase matrices
-(their data files are not part of the reference archive), Lambertian_surface mode, plotting and debug demos.
+(their data files are not part of the reference archive), plotting and debug demos.
 Those raise NotImplementedError rather than silently doing something else.
 """
 import argparse
@@ -154,8 +154,6 @@ class MonteCarlo(object):
             raise NotImplementedError('only spheres with the Henyey-Greenstein phase function are built for B200; '
                                       'the aspherical SSP / phase-matrix files are not part of the reference '
                                       'archive (README.md:40-42)')
-        if Lambertian_surface:
-            raise NotImplementedError('Lambertian_surface mode is not implemented in the B200 build')
         if debug:
             raise NotImplementedError('the two-scatter plotting demo (debug=True) is not part of the B200 build')
         if self.phase_functions:
@@ -188,7 +186,7 @@ class MonteCarlo(object):
 
         params = engine.make_params(self.theta_0, self.tau_tot, self.rho_snw, Lambertian_reflectance, wvl0, scale,
                                     k_first, lambert_bottom=bool(Lambertian_bottom),
-                                    n_theta_bins=int(self.n_theta_bins))
+                                    lambert_surface=bool(Lambertian_surface), n_theta_bins=int(self.n_theta_bins))
         par = self._parallel
         if par is None:
             par = self._parallel = Parallel(n_photon, devices=self.devices)

@@ -50,6 +50,9 @@ CASES = {
     # weakly absorbing visible ice, forward peaked, semi-infinite: thousands of events per photon
     'vis_long': (120, 0.5, 0.085, 250., 15., 19, 'const-vis', {}, dict(Lambertian_bottom=True,
                  Lambertian_reflectance=0.5), dict(ext_cff_mss_ice=6.6, ssa_ice=0.999989859099, g=0.89)),
+    # Lambertian_surface mode: the snow replaced by a Lambertian reflector (monte_carlo3D.py:1228-1250, 1385-1387)
+    'lambert_surface': (3000, 1.3, 0.085, 100., 40., 20, 'spectral', dict(tau_tot=5.0),
+                        dict(Lambertian_surface=True, Lambertian_bottom=False, Lambertian_reflectance=0.7), None),
     # isotropic scattering: the g == 0 branch of Henyey_Greenstein2 (monte_carlo3D.py:794-795)
     'isotropic': (1500, 0.5, 0.085, 100., 45., 17, 'const-kat', dict(tau_tot=5.0), dict(Lambertian_bottom=False),
                   dict(ssa_ice=0.9, g=0.0)),
@@ -92,6 +95,7 @@ def make_case(name, optics_root):
     cfg = dict(n_photon=n, wvl0=wvl0, half_width=hw, rds_snw=rds, theta_0=theta, seed=seed, fixture=kind,
                tau_tot=float(mkw.get('tau_tot', 1e6)), imp_cnc=float(mkw.get('imp_cnc', 0.0)), rho_snw=300.0,
                Lambertian_bottom=bool(rkw.get('Lambertian_bottom', True)),
+               Lambertian_surface=bool(rkw.get('Lambertian_surface', False)),
                Lambertian_reflectance=float(rkw.get('Lambertian_reflectance', 1.0)),
                preset=repr(preset))
     os.makedirs(GOLDEN_DIR, exist_ok=True)

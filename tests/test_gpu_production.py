@@ -78,6 +78,32 @@ def test_isotropic_and_backward_scattering_rows():
         assert same.mean() >= 0.9995, (g, same.mean())
 
 
+def test_lambertian_surface_mode():
+    # monte_carlo3D.py:1228-1250, 1385-1387: the snow replaced by a Lambertian reflector of reflectance R
+    from oracle import oracle
+    from monte_carlompi_b200 import post
+    rows = gpu_util.fixture_table('spectral', 100, 104, 156)
+    th = np.pi * 40. / 180.
+    n, R = 400000, 0.7
+    pe = engine.make_params(th, 5.0, 300., R, 1.3, SIGMA13, 104, lambert_bottom=False, lambert_surface=True, n_theta_bins=137)
+    po = oracle.make_params(th, 5.0, 300., R, 1.3, SIGMA13, 104, lambert_bottom=False, lambert_surface=True, n_theta_bins=137)
+    rec, tally, st = _run(pe, rows, 31, 0, n)
+    o = oracle.philox(po, rows, 31, 0, n, n_threads=os.cpu_count())
+    same = (rec['condition'] == o['condition']) & (rec['n_scat'] == o['n_scat']) & (rec['wvl_row'] == o['wvl_row'])
+    assert same.mean() >= 0.9995
+    refl = rec['condition'] == 1
+    assert abs(refl.mean() - R) < 4 * np.sqrt(R * (1 - R) / n) and set(np.unique(rec['condition'])) == {1, 4}
+    assert (rec['n_scat'][refl] >= 1).all() and (rec['n_scat'][~refl] == 0).all()
+    assert np.abs(rec['path_length'][refl]).max() < 1e-6          # nothing travelled inside the "snow"
+    a, b = rec['theta_n'][same & refl].astype(np.float64), o['theta_n'][same & refl]
+    assert np.percentile(np.abs(a - b), 99.9) < 1e-5
+    # a Lambertian reflector: BRF == R in every zenith bin (within noise), the normalisation check of brf()
+    mid, brf = post.brf_from_tally(tally, rows)
+    inner = slice(10, 127)
+    assert abs(np.mean(brf[inner]) - R) < 0.01 and np.std(brf[inner]) < 0.05
+    assert np.array_equal(tally, gpu_util.tally_from_records(rec, len(rows), 137))
+
+
 # ---------------------------------------------------------------------------------------------- 2. vs the reference
 def _stats_file():
     return os.path.join(gu.GOLDEN_DIR, 'stats_c2_reference.npz')
@@ -253,8 +279,6 @@ def test_argument_validation():
     bad['g'] = 1.0
     with pytest.raises(engine.Mc3dError):
         ctx.run(engine.make_params(0.1, 2.0, 300., 1.0, 0.5, 0.0, 50), bad, 1, 0, 10)
-    with pytest.raises(engine.Mc3dError):
-        ctx.run(engine.make_params(0.1, 2.0, 300., 1.0, 0.5, 0.0, 50, lambert_surface=True), rows, 1, 0, 10)
 
 
 def test_async_slots_overlap_and_match_sync():

@@ -15,7 +15,8 @@ pytestmark = pytest.mark.gpu
 def _replay(c):
     cfg = c['cfg']
     P = engine.make_params(np.pi * cfg['theta_0'] / 180., cfg['tau_tot'], cfg['rho_snw'], cfg['Lambertian_reflectance'],
-                           cfg['wvl0'], cfg['half_width'] / 2.355, 0, lambert_bottom=cfg['Lambertian_bottom'])
+                           cfg['wvl0'], cfg['half_width'] / 2.355, 0, lambert_bottom=cfg['Lambertian_bottom'],
+                           lambert_surface=cfg.get('Lambertian_surface', False))
     return gpu_util.context().replay(P, c['wvl'], c['ssa_ice'], c['ssa_imp'], c['g'], c['ext_cff_mss'], c['p_ext_imp'],
                                      c['init_draws'], c['offsets'], c['stream'])
 

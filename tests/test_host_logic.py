@@ -191,7 +191,7 @@ def test_out_of_scope_modes_raise(run_dir):
     with pytest.raises(NotImplementedError):
         mc.run(10, 1.3, 0.085, 100., shape='droxtal')
     with pytest.raises(NotImplementedError):
-        mc.run(10, 1.3, 0.085, 100., Lambertian_surface=True)
+        mc.run(10, 1.3, 0.085, 100., debug=True)
 
 
 def test_test_hook_presets_survive_run_attribute_overwrite(run_dir):

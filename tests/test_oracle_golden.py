@@ -9,7 +9,8 @@ from oracle import oracle
 
 def _params(cfg, **kw):
     return oracle.make_params(np.pi * cfg['theta_0'] / 180., cfg['tau_tot'], cfg['rho_snw'],
-                              cfg['Lambertian_reflectance'], lambert_bottom=cfg['Lambertian_bottom'], **kw)
+                              cfg['Lambertian_reflectance'], lambert_bottom=cfg['Lambertian_bottom'],
+                              lambert_surface=cfg.get('Lambertian_surface', False), **kw)
 
 
 @pytest.mark.parametrize('name', gu.CASES)
