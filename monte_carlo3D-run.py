@@ -82,10 +82,10 @@ def single_grain_size(n_photon, wvl, half_width, rds_snw, theta_0=0., stokes_par
 def multiple_grain_sizes(n_photon, wvl, half_width, rds_snw, theta_0=0., stokes_params=np.array([1, 0, 0, 0]),
                          shape='sphere', roughness='smooth'):
     monte_carlo_run = _model()
-    for i, rds in enumerate(rds_snw):
-        monte_carlo_run.run(n_photon, wvl, half_width, rds, theta_0=theta_0, stokes_params=stokes_params,
-                            shape=shape, roughness=roughness, debug=DEBUG, Lambertian_surface=LAMBERTIAN_SURFACE,
-                            Lambertian_bottom=LAMBERTIAN_BOTTOM, Lambertian_reflectance=LAMBERTIAN_REFLECTANCE)
+    # one case per grain size, several in flight on the GPU (the reference calls run() once per radius)
+    monte_carlo_run.run_sweep([dict(n_photon=n_photon, wvl0=wvl, half_width=half_width, rds_snw=rds, theta_0=theta_0,
+                                    Lambertian_surface=LAMBERTIAN_SURFACE, Lambertian_bottom=LAMBERTIAN_BOTTOM,
+                                    Lambertian_reflectance=LAMBERTIAN_REFLECTANCE) for rds in rds_snw])
     monte_carlo_run.close()
 
 

@@ -207,6 +207,86 @@ class MonteCarlo(object):
         output.write_run(output_file, all_answers, 1. / table['wvl_um'], self.snow_depth)
         print('%s' % output_file)   # for easy post processing
 
+    # ---- batched sweeps (reference monte_carlo3D-run.py:60-96, 112-122: one run() per wavelength / grain size) -----
+    def run_sweep(self, cases, write_output=True, seed=None):
+        """Run many cases with up to ``engine.N_SLOTS`` of them in flight on the GPU(s).
+
+        ``cases``: iterable of dicts with the arguments of ``run`` (``n_photon, wvl0, half_width, rds_snw`` and
+        optionally ``theta_0, Lambertian_bottom, Lambertian_reflectance, Lambertian_surface, test, seed``).  The
+        reference's sweep drivers call ``run`` once per (wavelength, grain size); here each case is enqueued on its
+        own slot / CUDA stream, so the long-walk tail, the copy-back and the text formatting of one case overlap
+        the walks of the next ones.  Results are identical to calling ``run`` case by case with the same seeds.
+        Returns the list of output paths (or of (records, tally, table) tuples when ``write_output`` is False)."""
+        cases = [dict(c) for c in cases]
+        if not cases:
+            return []
+        par = self._parallel
+        if par is None:
+            par = self._parallel = Parallel(cases[0]['n_photon'], devices=self.devices)
+        if par.size > 1:
+            return [self._run_case_serial(c, write_output, seed) for c in cases]     # one process per GPU: no slots
+        ctx = par.open()
+        depth = min(engine.N_SLOTS, len(cases))
+        n_max = max(int(c['n_photon']) for c in cases)
+        bufs = [engine.RecordBuffers(n_max) for _ in range(depth)]
+        pending = [None] * depth
+        results = [None] * len(cases)
+
+        def finish(slot):
+            k, c, table, tally, n = pending[slot]
+            stats = ctx.wait(slot)
+            rec = {name: col.copy() for name, col in bufs[slot].view(n).items()}
+            depth_m = ssp.snow_depth(table, self.tau_tot, self.rho_snw)
+            self.last_records, self.last_tally, self.last_table, self.last_stats = rec, tally, table, stats
+            if write_output:
+                self.snow_effective_radius = c['rds_snw']
+                self.theta_0 = (np.pi * c.get('theta_0', 0.)) / 180.
+                path = self.setup_output(n, c['wvl0'], c['half_width'])
+                output.write_run(path, rec, 1. / table['wvl_um'], depth_m)
+                print('%s' % path)
+                results[k] = path
+            else:
+                results[k] = (rec, tally, table)
+            pending[slot] = None
+
+        try:
+            for k, c in enumerate(cases):
+                slot = k % depth
+                if pending[slot] is not None:
+                    finish(slot)
+                n = int(c['n_photon'])
+                table, k_first, scale = self.build_table(c['wvl0'], c['half_width'], c['rds_snw'], test=c.get('test', False))
+                s = c.get('seed', seed if seed is not None else self.seed)
+                if s is None:
+                    s = int.from_bytes(os.urandom(8), 'little')
+                params = engine.make_params((np.pi * c.get('theta_0', 0.)) / 180., self.tau_tot, self.rho_snw,
+                                            c.get('Lambertian_reflectance', 1.), c['wvl0'], scale, k_first,
+                                            lambert_bottom=bool(c.get('Lambertian_bottom', True)),
+                                            lambert_surface=bool(c.get('Lambertian_surface', False)),
+                                            n_theta_bins=int(self.n_theta_bins))
+                tally = np.zeros((len(table), engine.N_COND + int(self.n_theta_bins)), np.uint64)
+                ctx.run_async(slot, params, table, int(s), 0, n, bufs[slot], tally)
+                pending[slot] = (k, c, table, tally, n)
+            for slot in sorted(range(depth), key=lambda sl: pending[sl][0] if pending[sl] else -1):
+                if pending[slot] is not None:
+                    finish(slot)
+        finally:
+            for slot in range(depth):
+                if pending[slot] is not None:
+                    try:
+                        ctx.wait(slot)
+                    except engine.Mc3dError:
+                        pass
+            for b in bufs:
+                b.free()
+        return results
+
+    def _run_case_serial(self, c, write_output, seed):
+        kw = {k: v for k, v in c.items() if k not in ('n_photon', 'wvl0', 'half_width', 'rds_snw')}
+        kw.setdefault('seed', seed)
+        self.run(c['n_photon'], c['wvl0'], c['half_width'], c['rds_snw'], write_output=write_output, **kw)
+        return (self.last_records, self.last_tally, self.last_table)
+
     def close(self):
         if self._parallel is not None:
             self._parallel.close()

@@ -57,3 +57,27 @@ def test_known_answer_through_the_driver(run_dir, optics_root):
     assert abs(trans - 0.66096) < 3.5 * np.sqrt(0.66 * 0.34 / n)
     assert mc.last_tally[:, 0].sum() == n
     mc.close()
+
+
+def test_sweep_equals_case_by_case_runs(run_dir, optics_root, capsys):
+    # reference monte_carlo3D-run.py:60-96: wavelengths x grain sizes, one run() each; here batched over the slots
+    cases = [dict(n_photon=30000 + 1000 * k, wvl0=w, half_width=hw, rds_snw=r, theta_0=th, Lambertian_bottom=True,
+                  Lambertian_reflectance=0.5, seed=100 + k)
+             for k, (w, hw, r, th) in enumerate([(1.3, 0.085, 50, 15.), (1.3, 0.085, 100, 15.), (1.55, 0.130, 250, 0.),
+                                                  (1.55, 0.130, 500, 30.), (0.9, 0.085, 1000, 60.), (2.2, 0.085, 100, 45.),
+                                                  (1.0, 0.085, 250, 15.), (1.3, 0.085, 1000, 15.), (1.8, 0.26, 100, 15.),
+                                                  (1.3, 1e-12, 100, 15.)])]
+    a = _model(run_dir, optics_root, tau_tot=8.0)
+    a.output_dir = str(run_dir / 'sweep')
+    paths = a.run_sweep(cases)
+    a.close()
+    assert len(paths) == len(cases) and len(set(paths)) == len(cases)
+    b = _model(run_dir, optics_root, tau_tot=8.0)
+    b.output_dir = str(run_dir / 'single')
+    for c, p in zip(cases, paths):
+        kw = {k: v for k, v in c.items() if k not in ('n_photon', 'wvl0', 'half_width', 'rds_snw')}
+        b.run(c['n_photon'], c['wvl0'], c['half_width'], c['rds_snw'], **kw)
+        q = capsys.readouterr().out.strip().splitlines()[-1]
+        assert os.path.basename(p) == os.path.basename(q)
+        assert open(p).read() == open(q).read()
+    b.close()
