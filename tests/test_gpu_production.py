@@ -155,6 +155,32 @@ def test_outcomes_and_brf_within_3_sigma_of_reference(optics_root):
     assert abs(mean_gpu - mean_ref) < 3.5 * np.sqrt(var_ref * (1.0 / n_ref + 1.0 / n_gpu))
 
 
+@pytest.mark.skipif(not os.path.isfile(_stats_file()), reason='reference statistics fixture not generated')
+def test_path_length_statistics_match_reference(optics_root):
+    # mean photon path length inside the slab (all photons, and reflected ones) against the reference at 10^6 photons
+    from monte_carlompi_b200 import ssp
+    z = np.load(_stats_file())
+    cfg = ast.literal_eval(str(z['config']))
+    n_ref = cfg['n_photon']
+    scale = cfg['half_width'] / 2.355
+    k_lo, k_hi = ssp.wavelength_grid(cfg['wvl0'], scale)
+    rows = ssp.build_table(optics_root[cfg['fixture']], 'mie_sot_ChC90_dns_1317.nc', cfg['rds_snw'], k_lo, k_hi, 0.0)
+    P = engine.make_params(np.pi * cfg['theta_0'] / 180., cfg['tau_tot'], 300., cfg['Lambertian_reflectance'], cfg['wvl0'],
+                           scale, k_lo, lambert_bottom=cfg['Lambertian_bottom'], n_theta_bins=cfg['n_theta_bins'])
+    n = 4000000
+    rec, _, _ = _run(P, rows, 424242, 0, n)
+    path = rec['path_length'].astype(np.float64)
+    mean_ref = float(z['path_sum']) / n_ref
+    var_ref = float(z['path_sq_sum']) / n_ref - mean_ref ** 2
+    assert abs(path.mean() - mean_ref) < 3.5 * np.sqrt(var_ref / n_ref + path.var() / n), (path.mean(), mean_ref)
+    refl = rec['condition'] == 1
+    n_refl_ref = int(z['counts'][:, 1].sum())
+    mean_refl_ref = float(z['path_sum_reflected']) / n_refl_ref
+    assert abs(path[refl].mean() - mean_refl_ref) < 3.5 * np.sqrt(path[refl].var() * (1.0 / n_refl_ref + 1.0 / refl.sum()))
+    # metres: tau / (ext rho) with ext ~ 16.4 m2/kg, rho 300 kg/m3 -> sub-centimetre paths at 1.3 um
+    assert 1e-3 < path.mean() < 5e-2
+
+
 def test_known_answers_van_de_hulst():
     # monte_carlo3D.py:1849-1852: tau 2, omega 0.9, g 0.75, mu0 1, black bottom: albedo 0.09739, transmittance 0.66096
     n = 8000000
@@ -201,6 +227,23 @@ def test_tallies_equal_histograms_of_the_records_full_size():
     assert (rec['theta_n'][refl] < np.pi / 2).all() and (rec['theta_n'] >= 0).all() and (rec['theta_n'] <= np.pi).all()
     assert (rec['phi_n'] >= 0).all() and (rec['phi_n'] <= np.float32(2 * np.pi)).all()
     assert (rec['phi_n'][rec['n_scat'] == 0] == 0).all() and (rec['path_length'] > 0).all()
+
+
+def test_full_size_properties_1e8_photons():
+    # BASELINE.json configs[3]-[4] sizes: tallies only; counts add up, chunking (2 chunks of 2^26 ids) and a range
+    # that crosses a multiple of 2^32 in the photon id give the same totals as the pieces
+    rows = gpu_util.fixture_table('spectral', 100, 104, 156)
+    P, _ = gpu_util.both_params(15., 1e6, 0.5, 1.3, SIGMA13, 104, True)
+    n = 100000000
+    begin = 2**32 - 30000000                      # crosses 2^32 inside the range
+    _, tally, st = _run(P, rows, 9, begin, n, records=False)
+    assert tally[:, 0].sum() == n and tally[:, 1:6].sum() == n and tally[:, 8:].sum() == tally[:, 1].sum()
+    assert st['n_photon'] == n and 60 * n < st['n_events'] < 70 * n
+    pieces = [(begin, 30000000), (2**32, 70000000)]
+    tsum = sum(_run(P, rows, 9, b, c, records=False)[1] for b, c in pieces)
+    assert np.array_equal(tsum, tally)
+    frac = tally[:, 1].sum() / float(n)
+    assert abs(frac - 0.4473) < 0.002            # reflected fraction of this configuration (reference: 0.4475 at 10^6)
 
 
 def test_results_do_not_depend_on_range_split_or_launch_shape():
