@@ -36,6 +36,7 @@ WORKLOAD = dict(wvl0=1.3, half_width=0.085, rds_snw=100, theta_0=15.0, tau_tot=1
                 lambert_bottom=True, r_lambert=0.5, n_theta_bins=137, fixture='spectral', seed=20190603)
 W_EVENT = 111.0   # algorithmic lane-instructions per scattering event
 NCU_TRAFFIC_BYTES_PER_PHOTON = 34.3   # measured once with ncu (profiles/), see roofline.traffic_is
+LOOP_CEILING_EVENTS_PER_S = 2.11e11   # tools/microbench/hotloop.cu: the event loop alone, all lanes busy, no refill (profiles/)
 
 
 def build_table():
@@ -314,6 +315,10 @@ def main():
                                     '%s' % (stats['sm_count'], f_mhz, 'median NVML sample under load' if clocks['sm_mhz'] else 'cudaDevAttrClockRate'),
                          'achieved_is': 'events per step / (timed region / steps), %d steps in flight' % depth,
                          'isolated_launch_ms': float(np.mean(iso_ms)), 'isolated_achieved': iso, 'isolated_frac': iso / peak,
+                         'measured_loop_ceiling': LOOP_CEILING_EVENTS_PER_S, 'frac_of_measured_loop_ceiling': ach / LOOP_CEILING_EVENTS_PER_S,
+                         'measured_loop_ceiling_is': 'events/s of the same event loop run alone on one B200 (no termination, no refill, 32/32 '
+                                                     'lanes, 8 warps per scheduler): half-rate ALU / IMAD.WIDE instructions cost two issue '
+                                                     'cycles, so 111 lane-instructions cost ~176 cycles (profiles/r01_microbench_hotloop.log)',
                          'traffic': NCU_TRAFFIC_BYTES_PER_PHOTON * n,
                          'traffic_is': 'dram__bytes_read.sum + dram__bytes_write.sum of the walk kernel from the ncu --set full '
                                        'capture at 1e6 photons per launch (profiles/r01_walk_bench_ncu_summary.csv: 34.3 MB), '

@@ -208,9 +208,13 @@ static bool build_rows(const mc3d_params *P, const mc3d_ssp_row *table, int n_ro
         d.one_m_g2 = (float)(1.0 - s.g * s.g);
         d.d_scale = (float)std::ldexp(2.0 * s.g, -32);
         d.d_off = (float)(1.0 - s.g + std::ldexp(s.g, -32));
-        d.flip = (s.g == 0.0) ? 0xffffffffu : 0u;
+        if (s.g == 0.0) { d.omr_scale = (float)std::ldexp(1.0, -32); d.omr_off = (float)std::ldexp(1.0, -33); }
+        else { d.omr_scale = -(float)std::ldexp(1.0, -32); d.omr_off = 1.0f; }
         threshold40(s.ssa_ice, &d.t_hi, &d.t_lo);
         threshold40(s.ssa_imp, &d.ti_hi, &d.ti_lo);
+        d.t_hot = std::min(d.t_hi, RENORM_WORD);
+        d.ti_hot = std::min(d.ti_hi, RENORM_WORD);
+        d.pad = 0u;
         // impurity iff (w + 1/2) 2^-32 <= P_ext_imp  <=>  w <= floor(P 2^32 - 1/2)
         const double sl = std::floor(std::ldexp(s.p_ext_imp, 32) - 0.5);
         if (sl >= 0.0) {

@@ -4,7 +4,7 @@
 //   Philox4x32-10, key = (seed_lo, seed_hi), counter = (c0, c1, pid_lo, pid_hi), pid = global photon id.
 //   c1 low byte is the stream tag:
 //     TAG_EVENT      c0 = event number i (1-based).  w0 -> r1 of Henyey_Greenstein2 (reference
-//                    monte_carlo3D.py:915-916), w1>>8 -> azimuth (921), w2 -> free path (1014),
+//                    monte_carlo3D.py:915-916), w1 -> azimuth (921), w2 -> free path (1014),
 //                    (w3<<8 | w1&0xff) -> 40-bit single-scatter-albedo variate (1020)
 //     TAG_SPECIES    c0 = i>>2, word i&3 -> ice/impurity choice (1023); drawn only when an impurity is present
 //     TAG_LAMBERT    c0 = i; sub-block 0 word 0 -> bottom reflectance draw (1422/1453); sub-block 1+(j>>1),
@@ -24,22 +24,28 @@ constexpr int N_COND = 8;
 
 // Per-wavelength row in the form the walk consumes (built on the host from mc3d_ssp_row, fp64 -> fp32/integer).
 struct DevRow {
-    // -- first 24 bytes: what the event loop loads (one 16-byte + one 8-byte shared-memory load)
+    // -- first 32 bytes: what the event loop loads (two 16-byte shared-memory loads)
     float one_m_g;    // 1 - g
     float one_m_g2;   // 1 - g^2
     float d_scale;    // 2 g 2^-32:      D = 1 - g + 2 g r = fma(float(w), d_scale, d_off), r = (w + 1/2) 2^-32
-    uint32_t flip;    // 0xffffffff when g == 0 (maps the factored HG form onto the reference's 1 - 2r branch)
-    uint32_t t_hi;    // ice: absorbed iff K40 >= T40 = ceil(ssa 2^40 - 1/2); t_hi = T40 >> 8 (saturated)
     float d_off;      // 1 - g + g 2^-32
+    uint32_t t_hot;   // coarse "needs attention" threshold on the absorption word: min(t_hi, 0xff000000).  It fires
+                      // on every possible absorption and, with probability >= 2^-8 per event, just to renormalise
+    float omr_scale;  // 1 - r = fma(float(w), omr_scale, omr_off): (-2^-32, 1).  For g == 0 rows (+2^-32, 2^-33),
+    float omr_off;    //   i.e. r itself, which maps the factored HG form onto the reference's `1 - 2r` branch
+    uint32_t ti_hot;  // t_hot of the impurity species
     // -- resolve / finalize only
+    uint32_t t_hi;    // ice: absorbed iff K40 >= T40 = ceil(ssa 2^40 - 1/2); t_hi = T40 >> 8 (saturated)
     uint32_t t_lo;    //      t_lo = T40 & 0xff, or 256 when T40 == 2^40 (never absorbed)
     uint32_t ti_hi;   // same for the impurity's single-scatter albedo
     uint32_t ti_lo;
     uint32_t s_last;  // impurity iff species word <= s_last (and s_any)
     uint32_t s_any;   // 0 when P_ext_imp == 0 (species word never selects the impurity)
     float inv_ext;    // ln 2 / (ext_cff_mss rho_snw): metres per unit of the walk's depth scale (optical depth / ln 2)
+    uint32_t pad;
 };
-static_assert(sizeof(DevRow) == 48, "DevRow is 48 bytes");
+static_assert(sizeof(DevRow) == 64, "DevRow is 64 bytes");
+constexpr uint32_t RENORM_WORD = 0xff000000u;   // an absorption word at/above this also triggers renormalisation
 
 // Raw result of one walk (32 B, one sector, written by the lane that finished the photon).
 struct __align__(16) RawResult {

@@ -26,16 +26,17 @@ __device__ __forceinline__ uint32_t lane_pid(const WalkParams &P, const Lane &L)
 // The part of a DevRow the hot loop needs: one 16-byte and one 4-byte shared-memory load per event (the loads are
 // issued before the Philox rounds and are off the critical path; keeping them out of registers buys occupancy).
 struct HotRow {
-    float one_m_g, one_m_g2, d_scale, d_off;
-    uint32_t flip, t_hi;
+    float one_m_g, one_m_g2, d_scale, d_off, omr_scale, omr_off;
+    uint32_t t_hot, ti_hot;
 };
 __device__ __forceinline__ uint32_t shared_address(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ HotRow load_hot_row(uint32_t row_addr)
 {
     HotRow h;
-    asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-        : "=f"(h.one_m_g), "=f"(h.one_m_g2), "=f"(h.d_scale), "=r"(h.flip) : "r"(row_addr));
-    asm("ld.shared.v2.u32 {%0, %1}, [%2+16];" : "=r"(h.t_hi), "=f"(h.d_off) : "r"(row_addr));
+    asm("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+        : "=f"(h.one_m_g), "=f"(h.one_m_g2), "=f"(h.d_scale), "=f"(h.d_off) : "r"(row_addr));
+    asm("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4+16];"
+        : "=r"(h.t_hot), "=f"(h.omr_scale), "=f"(h.omr_off), "=r"(h.ti_hot) : "r"(row_addr));
     return h;
 }
 
@@ -52,11 +53,11 @@ constexpr float LN2 = 0.6931471805599453f;
 // free path -ln(u) / ln 2 = -log2(u), u = (w + 0.5) 2^-32   (monte_carlo3D.py:1014, 1036), in the walk's depth unit
 __device__ __forceinline__ float free_path(uint32_t w) { return -lg2_fast(u32_to_unit(w)); }
 
-// cos, sin of the azimuth 2 pi u, u = ((w >> 8) + 0.5) 2^-24   (monte_carlo3D.py:921, 1258-1259).
+// cos, sin of the azimuth 2 pi u, u = (w + 0.5) 2^-32   (monte_carlo3D.py:921, 1258-1259).
 // Evaluated at 2 pi u - pi (inside the accurate range of sin/cos.approx) and negated.
 __device__ __forceinline__ void azimuth(uint32_t w, float &cp, float &sp)
 {
-    const float a = fmaf(__uint2float_rn(w >> 8), 3.7450702829239286e-07f, -3.1415922790826485f);
+    const float a = fmaf(__uint2float_rn(w), 1.4629180792671596e-09f, -3.1415926528583587f);
     cp = -cos_fast(a);
     sp = -sin_fast(a);
 }
@@ -88,9 +89,9 @@ __device__ __forceinline__ void scatter_and_move(Lane &L, const HotRow &H, const
 {
     // Henyey-Greenstein inverse CDF (790-800) in a cancellation-free form:
     //   D = 1 - g + 2 g r,  s = (1 - g^2)/D,  1 - cos = (1 - g)(1 - r)(s + 1 - g)/D,  sin^2 = (1 - cos)(1 + cos)
-    const float wf = __uint2float_rn(w.x ^ H.flip);
+    const float wf = __uint2float_rn(w.x);
     const float invD = rcp_fast(fmaf(wf, H.d_scale, H.d_off));          // D = 1 - g + 2 g r
-    const float omr = fmaf(wf, -2.3283064365386963e-10f, 1.0f);         // 1 - r
+    const float omr = fmaf(wf, H.omr_scale, H.omr_off);                 // 1 - r  (r itself for a g == 0 row)
     const float s = H.one_m_g2 * invD;
     const float omc = (H.one_m_g * invD) * (omr * (s + H.one_m_g));
     const float ct = 1.0f - omc;
@@ -116,11 +117,13 @@ __device__ __forceinline__ void scatter_and_move(Lane &L, const HotRow &H, const
     L.w3 = w.w;
 }
 
-// "Something may have happened": the photon left the slab, may have been absorbed (coarse 32-bit test), or is
-// due for its periodic renormalisation.  Everything behind this predicate is resolved later, by resolve().
+// "Something may have happened": the photon left the slab, or its absorption word is at/above the row's coarse
+// threshold t_hot = min(t_hi, 0xff000000) -- every possible absorption, plus a 2^-8 chance per event that only
+// serves to renormalise the direction and flush the path accumulator (a pseudo-random but per-photon deterministic
+// schedule, mean period <= 256 events, with no extra instruction in the loop).  Resolved later, by resolve().
 __device__ __forceinline__ bool needs_attention(const WalkParams &P, const Lane &L, uint32_t thi)
 {
-    return L.z > 0.0f || L.z < P.neg_tau_tot || L.w3 >= thi || (L.i & 255u) == 0u;
+    return L.z > 0.0f || L.z < P.neg_tau_tot || L.w3 >= thi;
 }
 
 // Resolve the reference's termination chain monte_carlo3D.py:1390-1466, in its order, for the event L.i that
@@ -180,7 +183,7 @@ __device__ __forceinline__ uint32_t resolve(const WalkParams &P, const DevRow &R
         }
         if (absorbed) cond = L.imp ? 5u : 4u;
     }
-    if (cond == ALIVE && (L.i & 255u) == 0u) {   // keyed on the photon's own event count: scheduling independent
+    if (cond == ALIVE && L.w3 >= RENORM_WORD) {   // keyed on the photon's own random stream: scheduling independent
         const float rn = rsqrt_fast(fmaf(L.ux, L.ux, fmaf(L.uy, L.uy, L.uz * L.uz)));
         L.ux *= rn; L.uy *= rn; L.uz *= rn;
         L.path_hi += L.path_lo;
@@ -199,11 +202,11 @@ __device__ __forceinline__ bool event(const WalkParams &P, const DevRow *rows, u
     const uint4 w = philox_event(L.i + 1u, phi, L.pk, P.rk);   // == philox4x32_10(i + 1, TAG_EVENT, plo, phi)
     L.i += 1u;
     scatter_and_move(L, H, w);
-    uint32_t thi = H.t_hi;
+    uint32_t thi = H.t_hot;
     if (IMP) {
         const DevRow &R = rows[lane_row(L, rows_addr)];
         L.imp = species_is_impurity(P, R, L.i, L.plo, phi);
-        thi = L.imp ? R.ti_hi : thi;
+        thi = L.imp ? H.ti_hot : thi;
     }
     return !needs_attention(P, L, thi);
 }

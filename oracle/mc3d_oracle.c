@@ -108,7 +108,7 @@ static void draw_event(draw_src *s, int64_t i, event_draws *d)
     uint32_t w[4];
     philox_block(s, (uint32_t)i, TAG_EVENT, w);
     d->r1 = u32_to_unit(w[0]);
-    d->u_phi = ((double)(w[1] >> 8) + 0.5) * (1.0 / 16777216.0);
+    d->u_phi = u32_to_unit(w[1]);
     d->u_tau = u32_to_unit(w[2]);
     uint64_t k40 = ((uint64_t)w[3] << 8) | (w[1] & 0xFFu);
     d->u_ssa = ((double)k40 + 0.5) * (1.0 / 1099511627776.0);
