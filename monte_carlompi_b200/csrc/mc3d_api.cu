@@ -426,7 +426,7 @@ int mc3d_set_launch(mc3d_ctx *ctx, int blocks_per_sm, int block_threads, int ref
 static int validate_run(const mc3d_params *P, const mc3d_ssp_row *table, int n_rows)
 {
     if (!P || !table) return fail(MC3D_EINVAL, "params / table is null");
-    if (n_rows < 1 || n_rows > 4096) return fail(MC3D_EINVAL, "n_rows %d out of range [1, 4096]", n_rows);
+    if (n_rows < 1 || n_rows > 2048) return fail(MC3D_EINVAL, "n_rows %d out of range [1, 2048] (rows are staged in shared memory)", n_rows);
     if (P->n_theta_bins < 0 || P->n_theta_bins > 65536) return fail(MC3D_EINVAL, "n_theta_bins out of range");
     if (!(P->tau_tot > 0.0)) return fail(MC3D_EINVAL, "tau_tot must be positive");
     if (!(P->rho_snw > 0.0)) return fail(MC3D_EINVAL, "rho_snw must be positive");

@@ -30,6 +30,9 @@ CASES = {
     # BASELINE.json configs[0] shape (driver defaults, monte_carlo3D-run.py:6-18, 48, 54, 84), fewer photons
     'c1_default': (2000, 1.3, 0.085, 100., 15., 20190603, 'spectral', {}, dict(Lambertian_bottom=True,
                    Lambertian_reflectance=0.5), None),
+    # BASELINE.json configs[0] at its full size: the driver default, n_photon = 10000
+    'c1_full_10k': (10000, 1.3, 0.085, 100., 15., 424242, 'spectral', {}, dict(Lambertian_bottom=True,
+                    Lambertian_reflectance=0.5), None),
     # finite slabs: Lambertian bottom reflections, direct / diffuse transmission
     'slab_tau3_lb': (1500, 1.3, 0.085, 100., 15., 11, 'spectral', dict(tau_tot=3.0), dict(Lambertian_bottom=True,
                      Lambertian_reflectance=0.5), None),

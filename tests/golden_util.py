@@ -8,7 +8,7 @@ import numpy as np
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 
 CASES = ('c1_default', 'slab_tau3_lb', 'slab_tau05_normal', 'slab_tau3_black', 'impurity', 'kat_vdh', 'vis_debug',
-         'isotropic', 'edge_of_table', 'vis_long', 'lambert_surface')
+         'isotropic', 'edge_of_table', 'vis_long', 'lambert_surface', 'c1_full_10k')
 
 
 def regenerate_stream(seed, n_photon, wvl0, half_width, n_walk_draws):
