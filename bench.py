@@ -70,21 +70,35 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.sm_max, self._stop_evt, self.active = index, [], set(), None, threading.Event(), False
 
+    def _sample(self):
+        import pynvml
+        self.samples.append(pynvml.nvmlDeviceGetClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+        for bit, name in self.REASONS.items():
+            if mask & bit:
+                self.reasons.add(name)
+
     def run(self):
         try:
             import pynvml
             pynvml.nvmlInit()
-            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
-            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+            self.ready = True
             while not self._stop_evt.is_set():
                 if self.active:
-                    self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
-                    mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                    for bit, name in self.REASONS.items():
-                        if mask & bit:
-                            self.reasons.add(name)
+                    self._sample()
                 time.sleep(0.02)
         except Exception as e:   # NVML missing: report that, never fake a clock
+            self.error = repr(e)
+
+    def sample_now(self):
+        """One sample from the calling thread while work is in flight (short timed regions may end between two
+        periodic samples)."""
+        try:
+            if getattr(self, 'ready', False) and self.active:
+                self._sample()
+        except Exception as e:
             self.error = repr(e)
 
     def stop(self):
@@ -213,6 +227,10 @@ def main():
     bufs = [engine.RecordBuffers(n) for _ in range(depth)]
     seed = WORKLOAD['seed']
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+
     def photon_begin(step):          # every (step, rank) walks its own id range: the whole job is distinct photons
         return (step * world + rank) * n
 
@@ -227,16 +245,13 @@ def main():
                 total += tallies[slot]
             ctx.run_async(slot, P, rows, seed, photon_begin(first_step + i), n, bufs[slot] if with_records else None,
                           tallies[slot])
+        sampler.sample_now()                         # the last `depth` steps are still running on the GPU here
         for i in range(max(0, n_steps - depth), n_steps):
             events += ctx.wait(i % depth)['n_events']
             total += tallies[i % depth]
         if world > 1:
             ctx.reduce_tally(total, root=0)          # the path's single collective: ncclReduce(sum, uint64)
         return events, total
-
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
 
     # ---- device-resident throughput ("value")
     pipeline(args.warmup, 0, False)
