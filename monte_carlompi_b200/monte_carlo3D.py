@@ -60,6 +60,7 @@ class MonteCarlo(object):
         for key, val in model_args_dict.items():
             setattr(self, key, val)
         self._parallel = None
+        self._rec_buf = None
         self.last_records = None
         self.last_tally = None
         self.last_table = None
@@ -192,7 +193,15 @@ class MonteCarlo(object):
             par = self._parallel = Parallel(n_photon, devices=self.devices)
         begin, count = par._map(n_photon)
         ctx = par.open()
-        records, tally, stats = ctx.run(params, table, self.last_seed, begin, count, records=True, tally=True)
+        # record columns land in page-locked host memory (copy-back at PCIe speed); the buffers are kept for reuse
+        if self._rec_buf is None or self._rec_buf.capacity < count:
+            if self._rec_buf is not None:
+                self._rec_buf.free()
+            self._rec_buf = engine.RecordBuffers(max(count, 1))
+        tally = np.zeros((len(table), engine.N_COND + int(self.n_theta_bins)), np.uint64)
+        ctx.run_async(0, params, table, self.last_seed, begin, count, self._rec_buf, tally)
+        stats = ctx.wait(0)
+        records = {name: col.copy() for name, col in self._rec_buf.view(count).items()}
         if par.size > 1:
             ctx.reduce_tally(tally, root=0)
         self.last_table, self.last_stats = table, stats
@@ -288,6 +297,9 @@ class MonteCarlo(object):
         return (self.last_records, self.last_tally, self.last_table)
 
     def close(self):
+        if self._rec_buf is not None:
+            self._rec_buf.free()
+            self._rec_buf = None
         if self._parallel is not None:
             self._parallel.close()
             self._parallel = None
