@@ -264,7 +264,7 @@ def main():
     sampler.active = False
 
     # ---- end to end through the C ABI with host buffers ("e2e")
-    pipeline(min(args.warmup, 4), args.warmup + args.steps, True)
+    pipeline(args.warmup, args.warmup + args.steps, True)
     barrier()
     sampler.active = True
     t0 = time.perf_counter()

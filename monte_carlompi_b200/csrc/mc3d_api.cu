@@ -29,8 +29,8 @@
 #include "mc3d_device.cuh"
 
 namespace mc3d {
-cudaError_t launch_walk(const WalkParams &P, bool impurity, int block_threads, int blocks_per_sm, int grid,
-                        cudaStream_t stream, int *occupancy);
+cudaError_t launch_walk(const WalkParams &P, bool impurity, int events_per_vote, int block_threads, int blocks_per_sm,
+                        int grid, cudaStream_t stream, int *occupancy);
 cudaError_t launch_init(const WalkParams &P, bool impurity, int sm_count, cudaStream_t stream);
 cudaError_t launch_finalize(const FinalizeParams &P, int sm_count, cudaStream_t stream);
 cudaError_t launch_replay(const ReplayParams &P, cudaStream_t stream);
@@ -174,6 +174,7 @@ struct mc3d_ctx {
     int rank = 0, world = 1;
     int blocks_per_sm = 0;   // 0 = automatic: enough lanes for >= 26 photons each, at most the resident capacity
     int block_threads = 256, refill_threshold = 4;
+    int events_per_vote = 0;   // 0 = chosen from the table (see auto_events_per_vote); MC3D_EVENTS_PER_VOTE overrides
     std::chrono::steady_clock::time_point t0[N_SLOTS];
     mc3d_stats pending_stats[N_SLOTS];
 };
@@ -228,6 +229,19 @@ static bool build_rows(const mc3d_params *P, const mc3d_ssp_row *table, int n_ro
         d.inv_ext = (float)(0.6931471805599453 / (s.ext_cff_mss * P->rho_snw));
     }
     return impurity;
+}
+
+// How many events a lane runs between two warp votes (walk_kernel's EPV): a performance-only choice.  Walks in
+// strongly absorbing or optically thin media last a few events, and a stopped lane should be noticed at once;
+// long walks amortise the vote over 4 events.  Judged from the co-albedo of the row at the band centre.
+static int auto_events_per_vote(const mc3d_params *P, const mc3d_ssp_row *table, int n_rows)
+{
+    int c = (int)std::lrint(P->wvl0_um * 100.0) - P->k_first;
+    c = std::max(0, std::min(n_rows - 1, c));
+    const double coalb = 1.0 - table[c].ssa_ice;
+    if (coalb >= 0.2 || P->tau_tot < 1.0 || (P->flags & MC3D_FLAG_LAMBERT_SURFACE)) return 1;
+    if (coalb >= 0.02 || P->tau_tot < 8.0) return 2;
+    return 4;
 }
 
 static void philox_round_keys(uint64_t seed, uint32_t rk[20])
@@ -292,6 +306,12 @@ static int init_device(Device &d, int id)
     return MC3D_OK;
 }
 
+static void apply_env(mc3d_ctx *ctx)
+{
+    const char *e = getenv("MC3D_EVENTS_PER_VOTE");   // experiments only; results do not depend on it
+    if (e && *e) ctx->events_per_vote = atoi(e);
+}
+
 int mc3d_create(mc3d_ctx **out, const int *device_ids, int n_dev)
 {
     if (!out) return fail(MC3D_EINVAL, "ctx out pointer is null");
@@ -321,6 +341,7 @@ int mc3d_create(mc3d_ctx **out, const int *device_ids, int n_dev)
             return fail(MC3D_ENCCL, "ncclCommInitAll failed: %s", g_nccl.GetErrorString(r));
         }
     }
+    apply_env(ctx);
     *out = ctx;
     return MC3D_OK;
 }
@@ -367,6 +388,7 @@ int mc3d_create_rank(mc3d_ctx **out, int device_id, const uint8_t nccl_id[128], 
             return fail(MC3D_ENCCL, "ncclCommInitRank failed: %s", g_nccl.GetErrorString(r));
         }
     }
+    apply_env(ctx);
     *out = ctx;
     return MC3D_OK;
 }
@@ -566,10 +588,11 @@ int mc3d_run_async(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, const mc3d
         // as keep >= 26 photons per lane (at most the resident capacity, at least one block per SM).  Small
         // launches then leave room for the next calls in flight on the other slots' streams.
         const int bps_variant = ctx->blocks_per_sm > 0 ? ctx->blocks_per_sm : 1024 / ctx->block_threads;
+        const int epv = ctx->events_per_vote > 0 ? ctx->events_per_vote : auto_events_per_vote(P, table, n_rows);
         int resident = 0;
         {
             WalkParams Wq = W;
-            CUDA_TRY(launch_walk(Wq, impurity, ctx->block_threads, bps_variant, 0, s.stream, &resident));
+            CUDA_TRY(launch_walk(Wq, impurity, epv, ctx->block_threads, bps_variant, 0, s.stream, &resident));
         }
         if (resident < 1) return fail(MC3D_ECUDA, "walk kernel does not fit on an SM (block %d, rows %d)", ctx->block_threads, n_rows);
         resident = std::min(resident, bps_variant);
@@ -595,7 +618,7 @@ int mc3d_run_async(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, const mc3d
             const int grid = std::max(1, std::min(st.grid_blocks, want));
             CUDA_TRY(cudaEventRecord(s.ev[2 * c], s.stream));
             CUDA_TRY(launch_init(Wc, impurity, d.sm_count, s.stream));
-            CUDA_TRY(launch_walk(Wc, impurity, ctx->block_threads, bps_variant, grid, s.stream, nullptr));
+            CUDA_TRY(launch_walk(Wc, impurity, epv, ctx->block_threads, bps_variant, grid, s.stream, nullptr));
             FinalizeParams F;
             memset(&F, 0, sizeof F);
             F.raw = s.raw.p;

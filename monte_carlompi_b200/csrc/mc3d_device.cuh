@@ -29,8 +29,8 @@ struct DevRow {
     float one_m_g2;   // 1 - g^2
     float d_scale;    // 2 g 2^-32:      D = 1 - g + 2 g r = fma(float(w), d_scale, d_off), r = (w + 1/2) 2^-32
     float d_off;      // 1 - g + g 2^-32
-    uint32_t t_hot;   // coarse "needs attention" threshold on the absorption word: min(t_hi, 0xff000000).  It fires
-                      // on every possible absorption and, with probability >= 2^-8 per event, just to renormalise
+    uint32_t t_hot;   // coarse "needs attention" threshold on the absorption word: min(t_hi, RENORM_WORD).  It fires
+                      // on every possible absorption and, with probability >= 2^-10 per event, just to renormalise
     float omr_scale;  // 1 - r = fma(float(w), omr_scale, omr_off): (-2^-32, 1).  For g == 0 rows (+2^-32, 2^-33),
     float omr_off;    //   i.e. r itself, which maps the factored HG form onto the reference's `1 - 2r` branch
     uint32_t ti_hot;  // t_hot of the impurity species
@@ -45,7 +45,7 @@ struct DevRow {
     uint32_t pad;
 };
 static_assert(sizeof(DevRow) == 64, "DevRow is 64 bytes");
-constexpr uint32_t RENORM_WORD = 0xff000000u;   // an absorption word at/above this also triggers renormalisation
+constexpr uint32_t RENORM_WORD = 0xffc00000u;   // an absorption word at/above this also triggers renormalisation (2^-10)
 
 // Raw result of one walk (32 B, one sector, written by the lane that finished the photon).
 struct __align__(16) RawResult {

@@ -118,9 +118,9 @@ __device__ __forceinline__ void scatter_and_move(Lane &L, const HotRow &H, const
 }
 
 // "Something may have happened": the photon left the slab, or its absorption word is at/above the row's coarse
-// threshold t_hot = min(t_hi, 0xff000000) -- every possible absorption, plus a 2^-8 chance per event that only
+// threshold t_hot = min(t_hi, RENORM_WORD) -- every possible absorption, plus a 2^-10 chance per event that only
 // serves to renormalise the direction and flush the path accumulator (a pseudo-random but per-photon deterministic
-// schedule, mean period <= 256 events, with no extra instruction in the loop).  Resolved later, by resolve().
+// schedule, mean period <= 1024 events, with no extra instruction in the loop).  Resolved later, by resolve().
 __device__ __forceinline__ bool needs_attention(const WalkParams &P, const Lane &L, uint32_t thi)
 {
     return L.z > 0.0f || L.z < P.neg_tau_tot || L.w3 >= thi;

@@ -32,7 +32,10 @@ struct WarpRing {
     uint4 entry[RING];   // Fresh{pid, row, dtau, pad}
 };
 
-template <bool IMP, int BLOCK, int MIN_BLOCKS>
+// EPV = events per lane between two warp votes (1, 2 or 4).  The vote + threshold test costs ~14 issue cycles per
+// iteration; a stopped lane idles < EPV events before it is noticed, so long walks want 4 and strongly absorbing
+// media (a few events per photon) want 1.  Results do not depend on it.
+template <bool IMP, int EPV, int BLOCK, int MIN_BLOCKS>
 __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) walk_kernel(const __grid_constant__ WalkParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -96,7 +99,9 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) walk_kernel(const __grid_co
             __syncwarp();
             if (exhausted) break;   // the ring is empty and the list has been handed out: drain
         }
-        if (alive) alive = event<IMP>(P, rows, rows_addr, L);
+#pragma unroll
+        for (int u = 0; u < EPV; ++u)
+            if (alive) alive = event<IMP>(P, rows, rows_addr, L);
     }
 
     // ---- phase B: drain.  Nothing left to hand out; every lane finishes the photon it carries.
@@ -114,11 +119,11 @@ size_t walk_smem_bytes(int n_rows, int block_threads)
     return ((n_rows * sizeof(DevRow) + 15) & ~size_t(15)) + (block_threads / 32) * sizeof(WarpRing);
 }
 
-template <bool IMP, int BLOCK, int MIN_BLOCKS>
+template <bool IMP, int EPV, int BLOCK, int MIN_BLOCKS>
 static cudaError_t launch_one(const WalkParams &P, int grid, cudaStream_t stream, int *occupancy)
 {
     const size_t smem = walk_smem_bytes(P.n_rows, BLOCK);
-    auto kern = walk_kernel<IMP, BLOCK, MIN_BLOCKS>;
+    auto kern = walk_kernel<IMP, EPV, BLOCK, MIN_BLOCKS>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     if (occupancy) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occupancy, kern, BLOCK, smem);
@@ -127,35 +132,35 @@ static cudaError_t launch_one(const WalkParams &P, int grid, cudaStream_t stream
 }
 
 template <int BLOCK, int MIN_BLOCKS>
-static cudaError_t launch_variant(const WalkParams &P, bool impurity, int grid, cudaStream_t stream, int *occupancy)
+static cudaError_t launch_variant(const WalkParams &P, bool impurity, int epv, int grid, cudaStream_t stream, int *occupancy)
 {
-    return impurity ? launch_one<true, BLOCK, MIN_BLOCKS>(P, grid, stream, occupancy)
-                    : launch_one<false, BLOCK, MIN_BLOCKS>(P, grid, stream, occupancy);
+    if (impurity) {
+        if (epv >= 4) return launch_one<true, 4, BLOCK, MIN_BLOCKS>(P, grid, stream, occupancy);
+        if (epv >= 2) return launch_one<true, 2, BLOCK, MIN_BLOCKS>(P, grid, stream, occupancy);
+        return launch_one<true, 1, BLOCK, MIN_BLOCKS>(P, grid, stream, occupancy);
+    }
+    if (epv >= 4) return launch_one<false, 4, BLOCK, MIN_BLOCKS>(P, grid, stream, occupancy);
+    if (epv >= 2) return launch_one<false, 2, BLOCK, MIN_BLOCKS>(P, grid, stream, occupancy);
+    return launch_one<false, 1, BLOCK, MIN_BLOCKS>(P, grid, stream, occupancy);
 }
 
-// block_threads in {128, 256, 512}; blocks_per_sm is the occupancy target the variant is compiled for
-// (56 / 53 / 48 / 40 registers per thread for <= 32 / 36 / 40 / 48 resident warps per SM; 32 warps is the default:
-// the loop is bound by the FMA pipe -- Philox's IMAD.WIDE -- and more resident warps do not raise its rate).
+// block_threads in {128, 256, 512}; blocks_per_sm is the occupancy target the variant is compiled for (56 / 48
+// registers per thread for <= 32 / 40 resident warps per SM; 32 warps is the default: the loop is bound by the
+// issue port -- Philox's half-rate integer instructions -- and more resident warps do not raise its rate).
 // With `occupancy` non-null nothing is launched; the resident blocks per SM are returned through it.
-cudaError_t launch_walk(const WalkParams &P, bool impurity, int block_threads, int blocks_per_sm, int grid,
-                        cudaStream_t stream, int *occupancy)
+cudaError_t launch_walk(const WalkParams &P, bool impurity, int events_per_vote, int block_threads, int blocks_per_sm,
+                        int grid, cudaStream_t stream, int *occupancy)
 {
     const int warps_per_sm = block_threads / 32 * blocks_per_sm;
     if (block_threads == 128) {
-        if (warps_per_sm <= 32) return launch_variant<128, 8>(P, impurity, grid, stream, occupancy);
-        if (warps_per_sm <= 36) return launch_variant<128, 9>(P, impurity, grid, stream, occupancy);
-        if (warps_per_sm <= 40) return launch_variant<128, 10>(P, impurity, grid, stream, occupancy);
-        return launch_variant<128, 12>(P, impurity, grid, stream, occupancy);
+        if (warps_per_sm <= 32) return launch_variant<128, 8>(P, impurity, events_per_vote, grid, stream, occupancy);
+        return launch_variant<128, 10>(P, impurity, events_per_vote, grid, stream, occupancy);
     }
     if (block_threads == 256) {
-        if (warps_per_sm <= 32) return launch_variant<256, 4>(P, impurity, grid, stream, occupancy);
-        if (warps_per_sm <= 40) return launch_variant<256, 5>(P, impurity, grid, stream, occupancy);
-        return launch_variant<256, 6>(P, impurity, grid, stream, occupancy);
+        if (warps_per_sm <= 32) return launch_variant<256, 4>(P, impurity, events_per_vote, grid, stream, occupancy);
+        return launch_variant<256, 5>(P, impurity, events_per_vote, grid, stream, occupancy);
     }
-    if (block_threads == 512) {
-        if (warps_per_sm <= 32) return launch_variant<512, 2>(P, impurity, grid, stream, occupancy);
-        return launch_variant<512, 3>(P, impurity, grid, stream, occupancy);
-    }
+    if (block_threads == 512) return launch_variant<512, 2>(P, impurity, events_per_vote, grid, stream, occupancy);
     return cudaErrorInvalidValue;
 }
 

@@ -269,9 +269,20 @@ def test_results_do_not_depend_on_range_split_or_launch_shape():
             for col in ref:
                 assert np.array_equal(rec[col], ref[col]), (col, bps, bt, thr)
             assert np.array_equal(t, tref)
+        # (c) events per warp vote (walk_kernel's EPV template parameter; chosen automatically in production)
+        for epv in ('1', '2', '4'):
+            os.environ['MC3D_EVENTS_PER_VOTE'] = epv
+            try:
+                with engine.Context([0]) as c2:
+                    rec, t, _ = c2.run(P, rows, seed, 0, n)
+            finally:
+                del os.environ['MC3D_EVENTS_PER_VOTE']
+            for col in ref:
+                assert np.array_equal(rec[col], ref[col]), (col, epv)
+            assert np.array_equal(t, tref)
     finally:
         ctx.set_launch(255, 256, 4)      # back to the automatic grid
-    # (c) a different seed gives a different realisation
+    # (d) a different seed gives a different realisation
     other, _, _ = ctx.run(P, rows, seed + 1, 0, n)
     assert (other['n_scat'] != ref['n_scat']).mean() > 0.5
 
