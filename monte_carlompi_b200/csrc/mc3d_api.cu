@@ -484,6 +484,7 @@ int mc3d_run_async(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, const mc3d
     memset(&W, 0, sizeof W);
     philox_round_keys(seed, W.rk);
     W.mu0x = (float)std::sin(P->theta0_rad);
+    if (W.mu0x == 0.0f) W.mu0x = -1e-15f;   // vertical incidence: see scatter_and_move (reproduces the muz_0 == -1 branch)
     W.mu0z = (float)(-std::cos(P->theta0_rad));
     W.tau_tot = (float)(P->tau_tot / 0.6931471805599453);   // the walk's depth unit is ln 2 optical depths
     W.neg_tau_tot = -W.tau_tot;

@@ -98,18 +98,17 @@ __device__ __forceinline__ void scatter_and_move(Lane &L, const HotRow &H, const
     const float st = sqrt_fast(omc * (2.0f - omc));
     float cp, sp;
     azimuth(w.y, cp, sp);
-    const float d2 = fmaf(L.ux, L.ux, L.uy * L.uy);
-    float nx, ny, nz;
-    if (d2 < 1e-24f) {   // travelling along +-z: the reference's muz_0 == +-1 branches (1262-1269)
-        const float sg = L.uz > 0.0f ? 1.0f : -1.0f;
-        nx = st * cp; ny = sg * st * sp; nz = sg * ct;
-    } else {             // 1270-1281
-        const float a = st * rsqrt_fast(d2);
-        const float uzc = L.uz * cp;
-        nx = fmaf(a, fmaf(L.ux, uzc, -L.uy * sp), L.ux * ct);
-        ny = fmaf(a, fmaf(L.uy, uzc, L.ux * sp), L.uy * ct);
-        nz = fmaf(-(d2 * a), cp, L.uz * ct);
-    }
+    // rotate the direction cosines, monte_carlo3D.py:1270-1281, with sqrt(1 - muz^2) taken as sqrt(mux^2 + muy^2).
+    // The reference's muz_0 == +-1 branches (1262-1269) need no code here: vertical incidence enters the walk as
+    // (-1e-15, 0, -1), for which this formula reproduces the muz_0 == -1 branch exactly (the host sets mu0x), and
+    // the step after a Lambertian reflection is taken in resolve().  The clamp only keeps a (never observed)
+    // exactly vertical direction finite.
+    const float d2 = fmaxf(fmaf(L.ux, L.ux, L.uy * L.uy), 1e-30f);
+    const float a = st * rsqrt_fast(d2);
+    const float uzc = L.uz * cp;
+    const float nx = fmaf(a, fmaf(L.ux, uzc, -L.uy * sp), L.ux * ct);
+    const float ny = fmaf(a, fmaf(L.uy, uzc, L.ux * sp), L.uy * ct);
+    const float nz = fmaf(-(d2 * a), cp, L.uz * ct);
     L.ux = nx; L.uy = ny; L.uz = nz;
     const float dtau = free_path(w.z);
     L.z = fmaf(dtau, nz, L.z);
