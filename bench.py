@@ -223,7 +223,7 @@ def main():
                            n_theta_bins=WORKLOAD['n_theta_bins'])
     n = args.photons
     n_rows = len(rows)
-    tallies = [np.zeros((n_rows, engine.N_COND + P.n_theta_bins), np.uint64) for _ in range(depth)]
+    tallies = [np.zeros((n_rows, P.tally_width), np.uint64) for _ in range(depth)]
     bufs = [engine.RecordBuffers(n) for _ in range(depth)]
     seed = WORKLOAD['seed']
 

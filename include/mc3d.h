@@ -61,7 +61,8 @@ typedef struct mc3d_params {
     int32_t k_first;     /* table row r holds wavelength (k_first + r) / 100 um (np.around(.., 2) grid)     */
     uint32_t flags;      /* MC3D_FLAG_*                                                                    */
     int32_t n_theta_bins;/* BRF zenith bins over [0, pi/2] (post_processing.py:73-76, 435-444); 0 = none   */
-    int32_t reserved;
+    int32_t n_phi_bins;  /* azimuth bins over [0, 2 pi] for a full-hemisphere (theta, phi) BRF; 0 or 1 = zenith
+                            only (the reference stores phi_n but never bins it)                               */
 } mc3d_params;
 
 /* One row of the per-wavelength SSP table, the de-duplicated form of the per-photon arrays the reference
@@ -144,9 +145,10 @@ int mc3d_host_free(void *ptr);
  *                   first / last row (cannot happen for a table covering +-7 sigma: |z| <= 6.8 with 32-bit
  *                   uniforms).
  *   records         NULL, or SoA destination for this call's photons (host memory, ideally mc3d_host_alloc'd).
- *   tally           NULL, or uint64[n_rows * (MC3D_N_COND + n_theta_bins)]: per row, outcome counts by
- *                   condition followed by the reflected-photon zenith histogram (np.histogram semantics of
- *                   post_processing.py:73-76 applied to float64(theta_n)).  OVERWRITTEN with this call's
+ *   tally           NULL, or uint64[n_rows * (MC3D_N_COND + n_theta_bins * max(1, n_phi_bins))]: per row, outcome
+ *                   counts by condition followed by the reflected-photon zenith histogram (np.histogram semantics
+ *                   of post_processing.py:73-76 applied to float64(theta_n)); with n_phi_bins > 1 each zenith bin
+ *                   is split into azimuth bins (np.histogram2d semantics, bin = theta_bin * n_phi_bins + phi_bin).  OVERWRITTEN with this call's
  *                   counts, reduced over all devices of the context; in a multi-rank context call
  *                   mc3d_reduce_tally afterwards for the job total.
  */

@@ -8,6 +8,8 @@
 //   outcome tallies by condition (calculate_albedo)           monte_carlo3D.py:1659-1671
 //   BRF zenith histogram of reflected photons, np.histogram(theta, bins=n, range=(0, pi/2))
 //                                                              post_processing.py:73-76
+//   optionally split in azimuth (np.histogram2d over (0, pi/2) x (0, 2 pi)): the full-hemisphere BRF the reference
+//   stores the data for (phi_n) but never bins
 // Tallies are integer counts per wavelength row (the wvn weights of the reference are applied on the host in
 // fp64), so they are exact and independent of the order of accumulation and of the GPU count.
 #include "mc3d_device.cuh"
@@ -31,7 +33,8 @@ template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK) finalize_kernel(const __grid_constant__ FinalizeParams P)
 {
     extern __shared__ unsigned int hist[];   // [n_rows][N_COND + n_theta_bins] when use_smem
-    const int stride = N_COND + P.n_theta_bins;
+    const int n_phi = P.n_phi_bins > 1 ? P.n_phi_bins : 1;
+    const int stride = N_COND + P.n_theta_bins * n_phi;
     const int hist_len = P.n_rows * stride;
     const bool tally = P.tally != nullptr;
     if (tally && P.use_smem) {
@@ -60,7 +63,13 @@ __global__ void __launch_bounds__(BLOCK) finalize_kernel(const __grid_constant__
         if (tally) {
             const int base = (int)row * stride;
             int bin = -1;
-            if (cond == 1u && P.n_theta_bins > 0) bin = histogram_bin((double)theta, P.n_theta_bins, P.edges);
+            if (cond == 1u && P.n_theta_bins > 0) {
+                bin = histogram_bin((double)theta, P.n_theta_bins, P.edges);
+                if (bin >= 0 && n_phi > 1) {   // np.histogram2d: a sample outside either range is dropped
+                    const int pb = histogram_bin((double)phi, n_phi, P.edges + P.n_theta_bins + 1);
+                    bin = pb >= 0 ? bin * n_phi + pb : -1;
+                }
+            }
             if (P.use_smem) {
                 atomicAdd(&hist[base], 1u);
                 atomicAdd(&hist[base + cond], 1u);
@@ -88,7 +97,7 @@ cudaError_t launch_finalize(const FinalizeParams &P, int sm_count, cudaStream_t 
 {
     constexpr int BLOCK = 256;
     FinalizeParams Q = P;
-    const size_t hist_bytes = (size_t)P.n_rows * (N_COND + P.n_theta_bins) * sizeof(unsigned int);
+    const size_t hist_bytes = (size_t)P.n_rows * (N_COND + (size_t)P.n_theta_bins * (P.n_phi_bins > 1 ? P.n_phi_bins : 1)) * sizeof(unsigned int);
     Q.use_smem = (P.tally != nullptr && hist_bytes <= 96 * 1024) ? 1 : 0;
     const size_t smem = Q.use_smem ? hist_bytes : 0;
     auto kern = finalize_kernel<BLOCK>;

@@ -450,6 +450,9 @@ static int validate_run(const mc3d_params *P, const mc3d_ssp_row *table, int n_r
     if (!P || !table) return fail(MC3D_EINVAL, "params / table is null");
     if (n_rows < 1 || n_rows > 2048) return fail(MC3D_EINVAL, "n_rows %d out of range [1, 2048] (rows are staged in shared memory)", n_rows);
     if (P->n_theta_bins < 0 || P->n_theta_bins > 65536) return fail(MC3D_EINVAL, "n_theta_bins out of range");
+    if (P->n_phi_bins < 0 || P->n_phi_bins > 4096) return fail(MC3D_EINVAL, "n_phi_bins out of range");
+    if ((uint64_t)n_rows * (N_COND + (uint64_t)P->n_theta_bins * std::max(1, P->n_phi_bins)) > (1ull << 28))
+        return fail(MC3D_EINVAL, "tally block too large (rows x zenith x azimuth bins)");
     if (!(P->tau_tot > 0.0)) return fail(MC3D_EINVAL, "tau_tot must be positive");
     if (!(P->rho_snw > 0.0)) return fail(MC3D_EINVAL, "rho_snw must be positive");
     if (!(P->theta0_rad >= 0.0 && P->theta0_rad < 1.5707963267948966))
@@ -462,10 +465,14 @@ static int validate_run(const mc3d_params *P, const mc3d_ssp_row *table, int n_r
     return MC3D_OK;
 }
 
+static int run_async_impl(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, const mc3d_ssp_row *table, int n_rows,
+                          uint64_t seed, uint64_t photon_begin, uint64_t n_photon, const mc3d_records *rec, uint64_t *tally);
+
 int mc3d_run_async(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, const mc3d_ssp_row *table, int n_rows,
                    uint64_t seed, uint64_t photon_begin, uint64_t n_photon, const mc3d_records *rec,
                    uint64_t *tally, mc3d_stats *stats)
 {
+    (void)stats;
     int rc = check_ctx(ctx);
     if (rc) return rc;
     if (slot_idx < 0 || slot_idx >= N_SLOTS) return fail(MC3D_EINVAL, "slot must be in [0, %d)", N_SLOTS);
@@ -473,12 +480,29 @@ int mc3d_run_async(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, const mc3d
     if (rc) return rc;
     for (Device &d : ctx->devs)
         if (d.slot[slot_idx].busy) return fail(MC3D_EINVAL, "slot %d is busy; call mc3d_wait first", slot_idx);
-    (void)stats;
+    rc = run_async_impl(ctx, slot_idx, P, table, n_rows, seed, photon_begin, n_photon, rec, tally);
+    if (rc) {
+        // a failure half way (allocation, launch, NCCL): drain whatever was enqueued and give the slot back, so the
+        // context stays usable and no copy into the caller's buffers is left in flight; the error text is kept
+        for (Device &d : ctx->devs) {
+            if (cudaSetDevice(d.id) == cudaSuccess && d.slot[slot_idx].stream) cudaStreamSynchronize(d.slot[slot_idx].stream);
+            d.slot[slot_idx].busy = false;
+        }
+        (void)cudaGetLastError();
+    }
+    return rc;
+}
+
+static int run_async_impl(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, const mc3d_ssp_row *table, int n_rows,
+                          uint64_t seed, uint64_t photon_begin, uint64_t n_photon, const mc3d_records *rec, uint64_t *tally)
+{
     ctx->t0[slot_idx] = std::chrono::steady_clock::now();
 
     const int n_dev = (int)ctx->devs.size();
-    const int stride = N_COND + P->n_theta_bins;
+    const int n_phi = std::max(1, P->n_phi_bins);
+    const size_t stride = N_COND + (size_t)P->n_theta_bins * n_phi;
     const size_t tally_len = (size_t)n_rows * stride;
+    const size_t n_edges = (size_t)P->n_theta_bins + 1 + (size_t)n_phi + 1;
 
     WalkParams W;
     memset(&W, 0, sizeof W);
@@ -530,7 +554,7 @@ int mc3d_run_async(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, const mc3d
 
         // ---- buffers
         CUDA_TRY(s.rows.ensure(n_rows));
-        CUDA_TRY(s.edges.ensure(P->n_theta_bins + 1));
+        CUDA_TRY(s.edges.ensure(n_edges));
         CUDA_TRY(s.counters.ensure(2 * std::max(n_chunks, 1)));
         CUDA_TRY(s.fresh.ensure(std::max<uint64_t>(chunk_cap, 1)));
         CUDA_TRY(s.raw.ensure(std::max<uint64_t>(chunk_cap, 1)));
@@ -547,11 +571,11 @@ int mc3d_run_async(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, const mc3d
             CUDA_TRY(cudaHostAlloc((void **)&s.host_rows, n_rows * sizeof(DevRow), cudaHostAllocPortable));
             s.host_rows_cap = n_rows;
         }
-        if (s.host_edges_cap < (size_t)P->n_theta_bins + 1) {
+        if (s.host_edges_cap < n_edges) {
             if (s.host_edges) cudaFreeHost(s.host_edges);
             s.host_edges = nullptr;
-            CUDA_TRY(cudaHostAlloc((void **)&s.host_edges, (P->n_theta_bins + 1) * sizeof(double), cudaHostAllocPortable));
-            s.host_edges_cap = P->n_theta_bins + 1;
+            CUDA_TRY(cudaHostAlloc((void **)&s.host_edges, n_edges * sizeof(double), cudaHostAllocPortable));
+            s.host_edges_cap = n_edges;
         }
         const bool want_rec = rec != nullptr;
         if (want_rec && cnt) {
@@ -578,8 +602,14 @@ int mc3d_run_async(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, const mc3d
         } else {
             s.host_edges[0] = 0.0;
         }
+        {   // azimuth edges np.linspace(0, 2 pi, n_phi + 1), stored after the zenith edges
+            double *pe = s.host_edges + P->n_theta_bins + 1;
+            const double stop = 6.283185307179586, step = stop / n_phi;
+            for (int b = 0; b <= n_phi; ++b) pe[b] = b * step;
+            pe[n_phi] = stop;
+        }
         CUDA_TRY(cudaMemcpyAsync(s.rows.p, s.host_rows, n_rows * sizeof(DevRow), cudaMemcpyHostToDevice, s.stream));
-        CUDA_TRY(cudaMemcpyAsync(s.edges.p, s.host_edges, (P->n_theta_bins + 1) * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+        CUDA_TRY(cudaMemcpyAsync(s.edges.p, s.host_edges, n_edges * sizeof(double), cudaMemcpyHostToDevice, s.stream));
         CUDA_TRY(cudaMemsetAsync(s.counters.p, 0, 2 * std::max(n_chunks, 1) * sizeof(uint32_t), s.stream));
         CUDA_TRY(cudaMemsetAsync(s.tally.p, 0, (tally_len + 1) * sizeof(unsigned long long), s.stream));
 
@@ -628,6 +658,7 @@ int mc3d_run_async(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, const mc3d
             F.n_photon = c_cnt;
             F.n_rows = n_rows;
             F.n_theta_bins = P->n_theta_bins;
+            F.n_phi_bins = P->n_phi_bins;
             if (want_rec) {
                 F.condition = rec->condition ? s.condition.p : nullptr;
                 F.wvl_row = rec->wvl_row ? s.wvl_row.p : nullptr;
@@ -720,10 +751,7 @@ int mc3d_run(mc3d_ctx *ctx, const mc3d_params *params, const mc3d_ssp_row *table
              mc3d_stats *stats)
 {
     int rc = mc3d_run_async(ctx, 0, params, table, n_rows, seed, photon_begin, n_photon, records, tally, stats);
-    if (rc) {
-        if (ctx) for (Device &d : ctx->devs) { cudaSetDevice(d.id); cudaStreamSynchronize(d.slot[0].stream); d.slot[0].busy = false; }
-        return rc;
-    }
+    if (rc) return rc;
     return mc3d_wait(ctx, 0, stats);
 }
 

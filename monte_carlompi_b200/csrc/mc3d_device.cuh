@@ -91,10 +91,11 @@ struct WalkParams {
 struct FinalizeParams {
     const RawResult *raw;
     const DevRow *rows;
-    const double *edges;     // [n_theta_bins + 1] = np.linspace(0, pi/2, n + 1)
+    const double *edges;     // [n_theta_bins + 1] = np.linspace(0, pi/2, n + 1), then [n_phi_bins + 1] = np.linspace(0, 2 pi, m + 1)
     uint32_t n_photon;
     int32_t n_rows;
     int32_t n_theta_bins;
+    int32_t n_phi_bins;      // <= 1: zenith histogram only
     int32_t use_smem;
     // record columns (device), any may be null
     uint8_t *condition;
@@ -103,7 +104,7 @@ struct FinalizeParams {
     float *phi_n;
     uint32_t *n_scat;
     float *path_length;
-    unsigned long long *tally;   // [n_rows][N_COND + n_theta_bins] or null
+    unsigned long long *tally;   // [n_rows][N_COND + n_theta_bins * max(1, n_phi_bins)] or null
     unsigned long long *n_events;
 };
 

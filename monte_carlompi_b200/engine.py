@@ -30,7 +30,12 @@ class Params(C.Structure):
     _fields_ = [('theta0_rad', C.c_double), ('tau_tot', C.c_double), ('rho_snw', C.c_double),
                 ('r_lambert', C.c_double), ('wvl0_um', C.c_double), ('sigma_um', C.c_double),
                 ('k_first', C.c_int32), ('flags', C.c_uint32), ('n_theta_bins', C.c_int32),
-                ('reserved', C.c_int32)]
+                ('n_phi_bins', C.c_int32)]
+
+    @property
+    def tally_width(self):
+        """uint64 entries per wavelength row of the tally block."""
+        return N_COND + self.n_theta_bins * max(1, self.n_phi_bins)
 
 
 class Records(C.Structure):
@@ -130,10 +135,10 @@ def nccl_unique_id():
 
 
 def make_params(theta0_rad, tau_tot, rho_snw, r_lambert, wvl0_um, sigma_um, k_first, lambert_bottom=True,
-                lambert_surface=False, n_theta_bins=0):
+                lambert_surface=False, n_theta_bins=0, n_phi_bins=0):
     flags = (FLAG_LAMBERT_BOTTOM if lambert_bottom else 0) | (FLAG_LAMBERT_SURFACE if lambert_surface else 0)
     return Params(float(theta0_rad), float(tau_tot), float(rho_snw), float(r_lambert), float(wvl0_um),
-                  float(sigma_um), int(k_first), flags, int(n_theta_bins), 0)
+                  float(sigma_um), int(k_first), flags, int(n_theta_bins), int(n_phi_bins))
 
 
 def py_repr(x):
@@ -244,7 +249,7 @@ class Context(object):
     # ---- production mode ------------------------------------------------------------------------------------
     def run_async(self, slot, params, table, seed, photon_begin, n_photon, records=None, tally=None):
         """Enqueue one walk.  ``records``: RecordBuffers, dict of numpy columns, or None.  ``tally``: uint64 array
-        of shape (n_rows, N_COND + n_theta_bins) or None.  Buffers must stay alive until ``wait(slot)``."""
+        of shape (n_rows, params.tally_width) or None.  Buffers must stay alive until ``wait(slot)``."""
         table = np.ascontiguousarray(table, dtype=ROW_DTYPE)
         rec_struct = None
         if isinstance(records, RecordBuffers):
@@ -254,7 +259,7 @@ class Context(object):
                                    for name, _ in RECORD_COLUMNS])
         if tally is not None:
             assert tally.dtype == np.uint64 and tally.flags.c_contiguous
-            assert tally.size == len(table) * (N_COND + params.n_theta_bins)
+            assert tally.size == len(table) * params.tally_width
         self._keep[slot] = (params, table, rec_struct, records, tally)
         _check(self._lib.mc3d_run_async(self._ctx, slot, C.byref(params), _ptr(table), len(table), int(seed),
                                         int(photon_begin), int(n_photon),
@@ -273,7 +278,7 @@ class Context(object):
         rec = None
         if records:
             rec = {name: np.empty(n_photon, dtype=dt) for name, dt in RECORD_COLUMNS}
-        t = np.zeros((len(table), N_COND + params.n_theta_bins), np.uint64) if tally else None
+        t = np.zeros((len(table), params.tally_width), np.uint64) if tally else None
         self.run_async(0, params, table, seed, photon_begin, n_photon, rec, t)
         stats = self.wait(0)
         return rec, t, stats

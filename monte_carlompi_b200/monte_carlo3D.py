@@ -35,7 +35,8 @@ class MonteCarlo(object):
             tau_tot, imp_cnc, rho_snw, rho_ice, rsensor, hsensor, flg_crt, flg_3D, output_dir, optics_dir,
             fi_imp, HG, phase_functions
             additional, B200 build only: seed (int, default: OS entropy like the unseeded reference),
-            devices (list of CUDA ordinals, default: all visible), n_theta_bins (BRF tally bins, default 137)
+            devices (list of CUDA ordinals, default: all visible), n_theta_bins (BRF tally bins, default 137),
+            n_phi_bins (azimuth bins of a full-hemisphere BRF tally, default 0 = zenith only)
         """
         model_args = self.get_model_args()
         model_args_dict = {'tau_tot': model_args.tau_tot,
@@ -53,7 +54,8 @@ class MonteCarlo(object):
                            'phase_functions': model_args.phase_functions,
                            'seed': None,
                            'devices': None,
-                           'n_theta_bins': DEFAULT_N_THETA_BINS}
+                           'n_theta_bins': DEFAULT_N_THETA_BINS,
+                           'n_phi_bins': 0}
         # kwargs given at instantiation win over config.ini / command line (monte_carlo3D.py:79-80)
         for kwarg, val in list(model_kwargs.items()):
             model_args_dict[kwarg] = val
@@ -187,7 +189,8 @@ class MonteCarlo(object):
 
         params = engine.make_params(self.theta_0, self.tau_tot, self.rho_snw, Lambertian_reflectance, wvl0, scale,
                                     k_first, lambert_bottom=bool(Lambertian_bottom),
-                                    lambert_surface=bool(Lambertian_surface), n_theta_bins=int(self.n_theta_bins))
+                                    lambert_surface=bool(Lambertian_surface), n_theta_bins=int(self.n_theta_bins),
+                                    n_phi_bins=int(self.n_phi_bins))
         par = self._parallel
         if par is None:
             par = self._parallel = Parallel(n_photon, devices=self.devices)
@@ -198,7 +201,7 @@ class MonteCarlo(object):
             if self._rec_buf is not None:
                 self._rec_buf.free()
             self._rec_buf = engine.RecordBuffers(max(count, 1))
-        tally = np.zeros((len(table), engine.N_COND + int(self.n_theta_bins)), np.uint64)
+        tally = np.zeros((len(table), params.tally_width), np.uint64)
         ctx.run_async(0, params, table, self.last_seed, begin, count, self._rec_buf, tally)
         stats = ctx.wait(0)
         records = {name: col.copy() for name, col in self._rec_buf.view(count).items()}
@@ -272,8 +275,8 @@ class MonteCarlo(object):
                                             c.get('Lambertian_reflectance', 1.), c['wvl0'], scale, k_first,
                                             lambert_bottom=bool(c.get('Lambertian_bottom', True)),
                                             lambert_surface=bool(c.get('Lambertian_surface', False)),
-                                            n_theta_bins=int(self.n_theta_bins))
-                tally = np.zeros((len(table), engine.N_COND + int(self.n_theta_bins)), np.uint64)
+                                            n_theta_bins=int(self.n_theta_bins), n_phi_bins=int(self.n_phi_bins))
+                tally = np.zeros((len(table), params.tally_width), np.uint64)
                 ctx.run_async(slot, params, table, int(s), 0, n, bufs[slot], tally)
                 pending[slot] = (k, c, table, tally, n)
             for slot in sorted(range(depth), key=lambda sl: pending[sl][0] if pending[sl] else -1):

@@ -27,7 +27,7 @@ def brf_from_tally(tally, table):
     h = wvn-weighted histogram of theta_n for condition == 1 over (0, pi/2); Q_down = sum of wvn over all photons;
     brf = h / (Q_down w), w = sin cos / sum(sin cos) at the bin midpoints."""
     tally = np.asarray(tally)
-    n_bins = tally.shape[1] - N_COND
+    n_bins = tally.shape[1] - N_COND      # zenith-only tally (n_phi_bins <= 1); see brf2d_from_tally otherwise
     wvn = _wvn(table)
     q_down = float((tally[:, 0].astype(np.float64) * wvn).sum())
     h = (tally[:, N_COND:].astype(np.float64) * wvn[:, None]).sum(axis=0)
@@ -35,6 +35,21 @@ def brf_from_tally(tally, table):
     midpoints = (np.diff(edges) / 2.) + edges[:-1]
     weights = np.sin(midpoints) * np.cos(midpoints) / np.sum(np.sin(midpoints) * np.cos(midpoints))
     return midpoints, h / (q_down * weights)
+
+
+def brf2d_from_tally(tally, table, n_theta_bins, n_phi_bins):
+    """Full-hemisphere BRF(theta, phi) from a tally taken with ``n_phi_bins`` azimuth bins: the same normalisation
+    as ``brf_from_tally`` with the zenith weight of a bin shared equally by its azimuth bins, so a Lambertian
+    reflector gives its reflectance in every (theta, phi) bin.  Returns (theta midpoints, phi midpoints, brf[theta, phi])."""
+    tally = np.asarray(tally)
+    wvn = _wvn(table)
+    q_down = float((tally[:, 0].astype(np.float64) * wvn).sum())
+    h = (tally[:, N_COND:].astype(np.float64) * wvn[:, None]).sum(axis=0).reshape(n_theta_bins, n_phi_bins)
+    te = np.linspace(0., np.pi / 2, n_theta_bins + 1)
+    pe = np.linspace(0., 2 * np.pi, n_phi_bins + 1)
+    tm, pm = (np.diff(te) / 2.) + te[:-1], (np.diff(pe) / 2.) + pe[:-1]
+    w = np.sin(tm) * np.cos(tm) / np.sum(np.sin(tm) * np.cos(tm)) / n_phi_bins
+    return tm, pm, h / (q_down * w[:, None])
 
 
 def brf_from_records(condition, wvn, theta_n, n_bins):

@@ -20,7 +20,7 @@ class Params(C.Structure):
     _fields_ = [('theta0_rad', C.c_double), ('tau_tot', C.c_double), ('rho_snw', C.c_double),
                 ('r_lambert', C.c_double), ('wvl0_um', C.c_double), ('sigma_um', C.c_double),
                 ('k_first', C.c_int32), ('flags', C.c_uint32), ('n_theta_bins', C.c_int32),
-                ('reserved', C.c_int32)]
+                ('n_phi_bins', C.c_int32)]   # unused by the oracle: its tallies are zenith-only
 
 
 ROW_DTYPE = np.dtype([('wvl_um', 'f8'), ('ssa_ice', 'f8'), ('ssa_imp', 'f8'), ('g', 'f8'),

@@ -33,13 +33,13 @@ def test_header_is_plain_c_and_struct_layouts_match(tmp_path):
     prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "mc3d.h"\nint main(void){'
                     'printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(mc3d_params), sizeof(mc3d_ssp_row),'
                     'sizeof(mc3d_records), sizeof(mc3d_records_f64), sizeof(mc3d_stats),'
-                    'offsetof(mc3d_params, k_first), offsetof(mc3d_params, n_theta_bins), offsetof(mc3d_stats, kernel_ms));'
+                    'offsetof(mc3d_params, k_first), offsetof(mc3d_params, n_phi_bins), offsetof(mc3d_stats, kernel_ms));'
                     'return 0;}\n')
     exe = tmp_path / 'layout'
     subprocess.check_call(['gcc', '-std=c99', '-pedantic', '-Werror', '-I', os.path.join(ROOT, 'include'), str(prog), '-o', str(exe)])
     got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
     want = [C.sizeof(engine.Params), engine.ROW_DTYPE.itemsize, C.sizeof(engine.Records), C.sizeof(engine.RecordsF64),
-            C.sizeof(engine.Stats), engine.Params.k_first.offset, engine.Params.n_theta_bins.offset,
+            C.sizeof(engine.Stats), engine.Params.k_first.offset, engine.Params.n_phi_bins.offset,
             engine.Stats.kernel_ms.offset]
     assert got == want
 

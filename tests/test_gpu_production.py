@@ -249,6 +249,36 @@ def test_full_size_properties_1e8_photons():
     assert abs(frac - f7) < 4 * np.sqrt(frac * (1 - frac) * (1e-7 + 1e-8))
 
 
+def test_full_hemisphere_theta_phi_tally_is_histogram2d_of_the_records():
+    # the reference stores phi_n but never bins it; with n_phi_bins > 1 the device splits every zenith bin in azimuth
+    from monte_carlompi_b200 import post
+    rows = gpu_util.fixture_table('spectral', 100, 104, 156)
+    n_t, n_p, n = 30, 24, 600000
+    P = engine.make_params(np.pi * 50. / 180., 1e6, 300., 0.5, 1.3, SIGMA13, 104, lambert_bottom=True, n_theta_bins=n_t, n_phi_bins=n_p)
+    rec, tally, _ = _run(P, rows, 77, 0, n)
+    assert tally.shape == (len(rows), engine.N_COND + n_t * n_p) and P.tally_width == engine.N_COND + n_t * n_p
+    refl = rec['condition'] == 1
+    want = np.zeros((len(rows), n_t * n_p), np.int64)
+    for r in range(len(rows)):
+        m = refl & (rec['wvl_row'] == r)
+        h2, _, _ = np.histogram2d(rec['theta_n'][m].astype(np.float64), rec['phi_n'][m].astype(np.float64), bins=(n_t, n_p),
+                                  range=((0., np.pi / 2), (0., 2 * np.pi)))
+        want[r] = h2.astype(np.int64).ravel()
+    assert np.array_equal(tally[:, engine.N_COND:].astype(np.int64), want)
+    # summing over azimuth gives the zenith-only tally of the same run
+    P1 = engine.make_params(np.pi * 50. / 180., 1e6, 300., 0.5, 1.3, SIGMA13, 104, lambert_bottom=True, n_theta_bins=n_t)
+    _, t1, _ = _run(P1, rows, 77, 0, n, records=False)
+    dropped = int(refl.sum()) - int(want.sum())                 # phi_n == float32(2 pi) lies outside [0, 2 pi]
+    assert 0 <= dropped <= 3
+    assert np.abs(tally[:, engine.N_COND:].reshape(len(rows), n_t, n_p).sum(axis=2).astype(np.int64)
+                  - t1[:, engine.N_COND:].astype(np.int64)).sum() == dropped
+    # oblique incidence (50 deg) + forward-peaked phase function: the BRF is brighter in the forward direction (phi ~ 0)
+    tm, pm, brf = post.brf2d_from_tally(tally, rows, n_t, n_p)
+    fwd = brf[20:28][:, [0, n_p - 1]].mean()
+    back = brf[20:28][:, [n_p // 2 - 1, n_p // 2]].mean()
+    assert fwd > 1.15 * back
+
+
 def test_results_do_not_depend_on_range_split_or_launch_shape():
     rows = gpu_util.fixture_table('spectral', 100, 104, 156)
     P, _ = gpu_util.both_params(15., 6.0, 0.5, 1.3, SIGMA13, 104, True)
