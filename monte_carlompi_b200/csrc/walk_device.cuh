@@ -210,6 +210,27 @@ __device__ __forceinline__ bool event(const WalkParams &P, const DevRow *rows, u
     return !needs_attention(P, L, thi);
 }
 
+// Latency-oriented form of event() for the drain phase, where a warp runs (almost) alone on its scheduler and the
+// dependent chain of one event, not the issue rate, sets the pace: `wn` holds the Philox block of event L.i + 1 on
+// entry and of the event after it on exit, so the next block's multiply chain overlaps this event's scattering math.
+template <bool IMP>
+__device__ __forceinline__ bool event_pipelined(const WalkParams &P, const DevRow *rows, uint32_t rows_addr, Lane &L, uint4 &wn)
+{
+    const HotRow H = load_hot_row(L.row_addr);
+    const uint32_t phi = (uint32_t)(P.photon_begin >> 32);
+    const uint4 w = wn;
+    wn = philox_event(L.i + 2u, phi, L.pk, P.rk);
+    L.i += 1u;
+    scatter_and_move(L, H, w);
+    uint32_t thi = H.t_hot;
+    if (IMP) {
+        const DevRow &R = rows[lane_row(L, rows_addr)];
+        L.imp = species_is_impurity(P, R, L.i, L.plo, phi);
+        thi = L.imp ? H.ti_hot : thi;
+    }
+    return !needs_attention(P, L, thi);
+}
+
 // Finish (store the raw record, free the lane) or resume a lane whose last event needed attention.
 template <bool IMP>
 __device__ __forceinline__ bool resolve_lane(const WalkParams &P, const DevRow *rows, uint32_t rows_addr, Lane &L)

@@ -104,11 +104,18 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) walk_kernel(const __grid_co
             if (alive) alive = event<IMP>(P, rows, rows_addr, L);
     }
 
-    // ---- phase B: drain.  Nothing left to hand out; every lane finishes the photon it carries.
+    // ---- phase B: drain.  Nothing left to hand out; every lane finishes the photon it carries.  The SM empties
+    // out, so this loop is latency-bound: it uses the software-pipelined event (next Philox block computed during
+    // the current event's math).
+    const uint32_t phi = (uint32_t)(P.photon_begin >> 32);
+    uint4 wn = philox_event(L.i + 1u, phi, L.pk, P.rk);
     for (;;) {
-        if (!alive && L.i != 0u) alive = resolve_lane<IMP>(P, rows, rows_addr, L);
+        if (!alive && L.i != 0u) {
+            alive = resolve_lane<IMP>(P, rows, rows_addr, L);
+            if (alive) wn = philox_event(L.i + 1u, phi, L.pk, P.rk);   // a Lambertian reflection advanced the event count
+        }
         if (__ballot_sync(0xffffffffu, alive) == 0u) break;
-        if (alive) alive = event<IMP>(P, rows, rows_addr, L);
+        if (alive) alive = event_pipelined<IMP>(P, rows, rows_addr, L, wn);
     }
 }
 
