@@ -113,6 +113,30 @@ class ClockSampler(threading.Thread):
                 'samples': len(self.samples)}
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this rank's CPU affinity to the NUMA node its GPU hangs off, before any pinned host memory is allocated,
+    so that record copy-back does not cross the socket interconnect.  Returns the node or None (no-op on failure)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        node = int(open('/sys/bus/pci/devices/%s/numa_node' % bus[-12:].lower()).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open('/sys/devices/system/node/node%d/cpulist' % node).read().strip().split(','):
+            lo, _, hi = part.partition('-')
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def cpu_port_rate(rows, k_lo, scale, photons, n_threads, begin=0):
     """Time the oracle's production-mode restatement (fp64, same Philox draws) on `photons` photon packets."""
     from oracle import oracle
@@ -186,6 +210,7 @@ def main():
     if not torch.cuda.is_available() or engine.device_count() == 0:
         raise SystemExit('bench.py: no CUDA device; the walk has no CPU fallback')
     torch.cuda.set_device(local_rank)
+    numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     nccl_id = None
     if world > 1:
         dist.init_process_group('cpu:gloo,cuda:nccl', rank=rank, world_size=world)
@@ -318,7 +343,7 @@ def main():
             'ms_per_step': 1e3 * T_a / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f32', 'data': 'synthetic',
             'config': workload_config(n, {'events_per_photon': events_a / float(args.steps * n), 'grid_blocks': stats['grid_blocks'],
-                                          'block_threads': stats['block_threads'], 'steps_in_flight': depth}),
+                                          'block_threads': stats['block_threads'], 'steps_in_flight': depth, 'rank0_numa_node': numa_node}),
             'clocks': clocks,
             'e2e': {'value': world * args.steps * n / T_e, 'unit': 'photons/s', 'events_per_s': sum_over_ranks(float(events_e)) / T_e
                     if world == 1 else None, 'ms_per_step': 1e3 * T_e / args.steps,
