@@ -113,6 +113,23 @@ typedef struct mc3d_stats {
     int32_t reserved;
 } mc3d_stats;
 
+/* Optional histograms of two per-photon columns, binned on the GPU so that no records have to leave it
+ * (post_processing.py:162-223: np.histogram(path_length * 100, bins=1000) and np.histogram(n_scat, bins=200), whose
+ * ranges are the data's own (min, max) -- obtained here from a first pass, see mc3d_extrema). */
+typedef struct mc3d_hist_spec {
+    int32_t n_scat_bins;  /* 0 = no n_scat histogram                                                        */
+    int32_t path_bins;    /* 0 = no path-length histogram                                                   */
+    double n_scat_lo, n_scat_hi; /* np.histogram range for float64(n_scat)                                  */
+    double path_lo, path_hi;     /* np.histogram range for float64(path_length) * path_scale                */
+    double path_scale;    /* 100 for centimetres (post_processing.py:169)                                   */
+} mc3d_hist_spec;
+
+/* Extrema over the photons of one call (all devices of the context); always computed. */
+typedef struct mc3d_extrema {
+    uint32_t n_scat_min, n_scat_max;
+    float path_min, path_max; /* metres */
+} mc3d_extrema;
+
 /* ---- library / device discovery ---------------------------------------------------------------------- */
 int mc3d_abi_version(void);
 const char *mc3d_last_error(void);
@@ -169,6 +186,15 @@ int mc3d_wait(mc3d_ctx *ctx, int slot, mc3d_stats *stats);
 /* Sum `tally` (uint64[n]) over the ranks of a multi-rank context with one ncclReduce to `root`
  * (replaces comm.gather for the reduced quantities, parallelize.py:19).  In place; no-op for world_size 1. */
 int mc3d_reduce_tally(mc3d_ctx *ctx, uint64_t *tally, uint64_t n, int root);
+
+/* Histograms (see mc3d_hist_spec).  mc3d_set_histograms configures the context: every later mc3d_run /
+ * mc3d_run_async also bins its photons with np.histogram's uniform-bin semantics (NULL switches it off again; the
+ * spec is copied).  mc3d_get_histograms, called after mc3d_wait / mc3d_run and before the slot is reused, copies
+ * out the counts of that call summed over the context's devices -- n_scat_counts: uint64[n_scat_bins],
+ * path_counts: uint64[path_bins], either may be NULL -- and the extrema (may be NULL).  In a multi-rank context sum
+ * the counts with mc3d_reduce_tally and combine the extrema on the host. */
+int mc3d_set_histograms(mc3d_ctx *ctx, const mc3d_hist_spec *spec);
+int mc3d_get_histograms(mc3d_ctx *ctx, int slot, uint64_t *n_scat_counts, uint64_t *path_counts, mc3d_extrema *extrema);
 
 /* Replay mode (fp64 walk that consumes the reference's own recorded random stream; correctness tool).
  * Per-photon inputs are the arrays the reference holds at monte_carlo3D.py:1575-1612: wvl, ssa_ice, ssa_imp,

@@ -10,6 +10,8 @@
 //                                                              post_processing.py:73-76
 //   optionally split in azimuth (np.histogram2d over (0, pi/2) x (0, 2 pi)): the full-hemisphere BRF the reference
 //   stores the data for (phi_n) but never bins
+//   optional histograms of n_scat and of path_length * scale over caller-given ranges, np.histogram(x, bins=n)
+//                                                              post_processing.py:162-223
 // Tallies are integer counts per wavelength row (the wvn weights of the reference are applied on the host in
 // fp64), so they are exact and independent of the order of accumulation and of the GPU count.
 #include "mc3d_device.cuh"
@@ -37,11 +39,16 @@ __global__ void __launch_bounds__(BLOCK) finalize_kernel(const __grid_constant__
     const int stride = N_COND + P.n_theta_bins * n_phi;
     const int hist_len = P.n_rows * stride;
     const bool tally = P.tally != nullptr;
-    if (tally && P.use_smem) {
-        for (int k = threadIdx.x; k < hist_len; k += BLOCK) hist[k] = 0u;
+    // the optional column histograms sit behind the tally block in shared memory
+    const int xh_len = P.hist ? P.n_scat_bins + P.path_bins : 0;
+    unsigned int *xh = hist + (tally && P.use_smem ? hist_len : 0);
+    if ((tally && P.use_smem) || (xh_len && P.hist_smem)) {
+        const int len = (tally && P.use_smem ? hist_len : 0) + (P.hist_smem ? xh_len : 0);
+        for (int k = threadIdx.x; k < len; k += BLOCK) hist[k] = 0u;
         __syncthreads();
     }
     unsigned long long events = 0ull;
+    uint32_t ns_min = 0xffffffffu, ns_max = 0u, pl_min = 0xffffffffu, pl_max = 0u;
     for (uint32_t p = blockIdx.x * BLOCK + threadIdx.x; p < P.n_photon; p += gridDim.x * BLOCK) {
         const RawResult *src = P.raw + p;
         const float4 a = *reinterpret_cast<const float4 *>(src);
@@ -58,8 +65,27 @@ __global__ void __launch_bounds__(BLOCK) finalize_kernel(const __grid_constant__
         if (P.theta_n) P.theta_n[p] = theta;
         if (P.phi_n) P.phi_n[p] = phi;
         if (P.n_scat) P.n_scat[p] = b.x;
-        if (P.path_length) P.path_length[p] = a.w * P.rows[row].inv_ext;
+        const float path_m = a.w * P.rows[row].inv_ext;
+        if (P.path_length) P.path_length[p] = path_m;
         events += (unsigned long long)b.x + 1ull;
+        ns_min = min(ns_min, b.x);
+        ns_max = max(ns_max, b.x);
+        pl_min = min(pl_min, __float_as_uint(path_m));
+        pl_max = max(pl_max, __float_as_uint(path_m));
+        if (xh_len) {
+            int hb[2] = {-1, -1};
+            if (P.n_scat_bins > 0) hb[0] = histogram_bin((double)b.x, P.n_scat_bins, P.hist_edges);
+            if (P.path_bins > 0) {
+                hb[1] = histogram_bin(__dmul_rn((double)path_m, P.path_scale), P.path_bins, P.hist_edges + P.n_scat_bins + 1);
+                if (hb[1] >= 0) hb[1] += P.n_scat_bins;
+            }
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                if (hb[k] < 0) continue;
+                if (P.hist_smem) atomicAdd(&xh[hb[k]], 1u);
+                else atomicAdd(&P.hist[hb[k]], 1ull);
+            }
+        }
         if (tally) {
             const int base = (int)row * stride;
             int bin = -1;
@@ -84,11 +110,29 @@ __global__ void __launch_bounds__(BLOCK) finalize_kernel(const __grid_constant__
     // events: warp reduce, one atomic per warp
     for (int o = 16; o > 0; o >>= 1) events += __shfl_xor_sync(0xffffffffu, events, o);
     if ((threadIdx.x & 31) == 0 && events) atomicAdd(P.n_events, events);
+    if (P.extrema) {
+        ns_min = __reduce_min_sync(0xffffffffu, ns_min);
+        ns_max = __reduce_max_sync(0xffffffffu, ns_max);
+        pl_min = __reduce_min_sync(0xffffffffu, pl_min);
+        pl_max = __reduce_max_sync(0xffffffffu, pl_max);
+        if ((threadIdx.x & 31) == 0 && ns_min <= ns_max) {
+            atomicMax(&P.extrema[0], ~ns_min);   // minima are stored complemented: the buffer starts as zeros
+            atomicMax(&P.extrema[1], ns_max);
+            atomicMax(&P.extrema[2], ~pl_min);
+            atomicMax(&P.extrema[3], pl_max);
+        }
+    }
+    if ((tally && P.use_smem) || (xh_len && P.hist_smem)) __syncthreads();
     if (tally && P.use_smem) {
-        __syncthreads();
         for (int k = threadIdx.x; k < hist_len; k += BLOCK) {
             const unsigned int v = hist[k];
             if (v) atomicAdd(&P.tally[k], (unsigned long long)v);
+        }
+    }
+    if (xh_len && P.hist_smem) {
+        for (int k = threadIdx.x; k < xh_len; k += BLOCK) {
+            const unsigned int v = xh[k];
+            if (v) atomicAdd(&P.hist[k], (unsigned long long)v);
         }
     }
 }
@@ -99,14 +143,16 @@ cudaError_t launch_finalize(const FinalizeParams &P, int sm_count, cudaStream_t 
     FinalizeParams Q = P;
     const size_t hist_bytes = (size_t)P.n_rows * (N_COND + (size_t)P.n_theta_bins * (P.n_phi_bins > 1 ? P.n_phi_bins : 1)) * sizeof(unsigned int);
     Q.use_smem = (P.tally != nullptr && hist_bytes <= 96 * 1024) ? 1 : 0;
-    const size_t smem = Q.use_smem ? hist_bytes : 0;
+    const size_t xh_bytes = P.hist ? ((size_t)P.n_scat_bins + (size_t)P.path_bins) * sizeof(unsigned int) : 0;
+    Q.hist_smem = (xh_bytes > 0 && xh_bytes <= 64 * 1024) ? 1 : 0;
+    const size_t smem = (Q.use_smem ? hist_bytes : 0) + (Q.hist_smem ? xh_bytes : 0);
     auto kern = finalize_kernel<BLOCK>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
     long long want = ((long long)P.n_photon + BLOCK - 1) / BLOCK;
-    const int per_sm = smem > 56 * 1024 ? 2 : 4;
+    const int per_sm = smem > 112 * 1024 ? 1 : (smem > 56 * 1024 ? 2 : 4);
     int grid = (int)(want < (long long)sm_count * per_sm ? (want > 0 ? want : 1) : (long long)sm_count * per_sm);
     kern<<<grid, BLOCK, smem, stream>>>(Q);
     return cudaGetLastError();

@@ -145,6 +145,12 @@ struct Slot {
     DevBuf<float> theta_n, phi_n, path_length;
     DevBuf<uint32_t> n_scat;
     DevBuf<unsigned long long> tally;       // + 1 trailing element: n_events
+    DevBuf<unsigned long long> extras;      // [0..1]: 4 x uint32 extrema, then the optional n_scat / path histograms
+    unsigned long long *host_extras = nullptr;  // pinned mirror
+    size_t host_extras_cap = 0, extras_len = 0;
+    DevBuf<double> hist_edges;
+    double *host_hist_edges = nullptr;
+    size_t host_hist_edges_cap = 0;
     unsigned long long *host_tally = nullptr;   // pinned mirror of `tally`
     size_t host_tally_cap = 0;
     DevRow *host_rows = nullptr;            // pinned staging for the row upload
@@ -177,6 +183,13 @@ struct mc3d_ctx {
     int events_per_vote = 0;   // 0 = chosen from the table (see auto_events_per_vote); MC3D_EVENTS_PER_VOTE overrides
     std::chrono::steady_clock::time_point t0[N_SLOTS];
     mc3d_stats pending_stats[N_SLOTS];
+    bool hist_on = false;
+    mc3d_hist_spec hist_spec{};
+    // results of the last completed call of each slot (combined over devices in mc3d_wait)
+    mc3d_hist_spec done_spec[N_SLOTS]{};
+    bool done_hist[N_SLOTS] = {};
+    mc3d_extrema done_extrema[N_SLOTS]{};
+    std::vector<uint64_t> done_counts[N_SLOTS];
 };
 
 // ------------------------------------------------------------------------------------------------ helpers
@@ -242,6 +255,14 @@ static int auto_events_per_vote(const mc3d_params *P, const mc3d_ssp_row *table,
     if (coalb >= 0.2 || P->tau_tot < 1.0 || (P->flags & MC3D_FLAG_LAMBERT_SURFACE)) return 1;
     if (coalb >= 0.02 || P->tau_tot < 8.0) return 2;
     return 4;
+}
+
+// np.linspace(start, stop, n + 1): arange * step + start with the endpoint forced (numpy/_core/function_base.py)
+static void linspace_edges(double start, double stop, int n_bins, double *out)
+{
+    const double step = (stop - start) / n_bins;
+    for (int b = 0; b <= n_bins; ++b) out[b] = b * step + start;
+    out[n_bins] = stop;
 }
 
 static void philox_round_keys(uint64_t seed, uint32_t rk[20])
@@ -404,7 +425,9 @@ int mc3d_destroy(mc3d_ctx *ctx)
             if (s.stream) cudaStreamSynchronize(s.stream);
             s.rows.release(); s.edges.release(); s.counters.release(); s.fresh.release(); s.raw.release(); s.condition.release();
             s.wvl_row.release(); s.theta_n.release(); s.phi_n.release(); s.path_length.release();
-            s.n_scat.release(); s.tally.release();
+            s.n_scat.release(); s.tally.release(); s.extras.release(); s.hist_edges.release();
+            if (s.host_extras) cudaFreeHost(s.host_extras);
+            if (s.host_hist_edges) cudaFreeHost(s.host_hist_edges);
             if (s.host_tally) cudaFreeHost(s.host_tally);
             if (s.host_rows) cudaFreeHost(s.host_rows);
             if (s.host_edges) cudaFreeHost(s.host_edges);
@@ -525,6 +548,9 @@ static int run_async_impl(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, con
     threshold40(P->r_lambert, &W.surf_t_hi, &W.surf_t_lo);
     W.refill_threshold = (uint32_t)ctx->refill_threshold;
 
+    ctx->done_hist[slot_idx] = ctx->hist_on;
+    ctx->done_spec[slot_idx] = ctx->hist_spec;
+
     mc3d_stats &st = ctx->pending_stats[slot_idx];
     memset(&st, 0, sizeof st);
     st.n_devices = n_dev;
@@ -577,6 +603,34 @@ static int run_async_impl(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, con
             CUDA_TRY(cudaHostAlloc((void **)&s.host_edges, n_edges * sizeof(double), cudaHostAllocPortable));
             s.host_edges_cap = n_edges;
         }
+        const bool hist_on = ctx->hist_on;
+        const mc3d_hist_spec hs = ctx->hist_spec;
+        const size_t n_hist = hist_on ? (size_t)hs.n_scat_bins + (size_t)hs.path_bins : 0;
+        const size_t n_hist_edges = hist_on ? n_hist + 2 : 0;
+        s.extras_len = 2 + n_hist;
+        CUDA_TRY(s.extras.ensure(s.extras_len));
+        if (s.host_extras_cap < s.extras_len) {
+            if (s.host_extras) cudaFreeHost(s.host_extras);
+            s.host_extras = nullptr;
+            CUDA_TRY(cudaHostAlloc((void **)&s.host_extras, s.extras_len * sizeof(unsigned long long), cudaHostAllocPortable));
+            s.host_extras_cap = s.extras_len;
+        }
+        if (hist_on) {
+            CUDA_TRY(s.hist_edges.ensure(n_hist_edges));
+            if (s.host_hist_edges_cap < n_hist_edges) {
+                if (s.host_hist_edges) cudaFreeHost(s.host_hist_edges);
+                s.host_hist_edges = nullptr;
+                CUDA_TRY(cudaHostAlloc((void **)&s.host_hist_edges, n_hist_edges * sizeof(double), cudaHostAllocPortable));
+                s.host_hist_edges_cap = n_hist_edges;
+            }
+            if (hs.n_scat_bins > 0) linspace_edges(hs.n_scat_lo, hs.n_scat_hi, hs.n_scat_bins, s.host_hist_edges);
+            else s.host_hist_edges[0] = 0.0;
+            if (hs.path_bins > 0) linspace_edges(hs.path_lo, hs.path_hi, hs.path_bins, s.host_hist_edges + hs.n_scat_bins + 1);
+            else s.host_hist_edges[hs.n_scat_bins + 1] = 0.0;
+            CUDA_TRY(cudaMemcpyAsync(s.hist_edges.p, s.host_hist_edges, n_hist_edges * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+        }
+        // extrema (the minima are kept complemented, so everything starts at 0) and histogram counts
+        CUDA_TRY(cudaMemsetAsync(s.extras.p, 0, s.extras_len * sizeof(unsigned long long), s.stream));
         const bool want_rec = rec != nullptr;
         if (want_rec && cnt) {
             if (rec->condition) CUDA_TRY(s.condition.ensure(chunk_cap));
@@ -669,6 +723,14 @@ static int run_async_impl(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, con
             }
             F.tally = s.tally.p;
             F.n_events = s.tally.p + tally_len;
+            F.extrema = reinterpret_cast<uint32_t *>(s.extras.p);
+            if (n_hist) {
+                F.hist = s.extras.p + 2;
+                F.hist_edges = s.hist_edges.p;
+                F.n_scat_bins = hs.n_scat_bins;
+                F.path_bins = hs.path_bins;
+                F.path_scale = hs.path_scale;
+            }
             CUDA_TRY(launch_finalize(F, d.sm_count, s.stream));
             CUDA_TRY(cudaEventRecord(s.ev[2 * c + 1], s.stream));
             if (want_rec) {
@@ -685,6 +747,7 @@ static int run_async_impl(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, con
 #undef COPY_COL
             }
         }
+        CUDA_TRY(cudaMemcpyAsync(s.host_extras, s.extras.p, s.extras_len * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
         s.busy = true;
         s.n_photon = cnt;
         s.tally_len = tally_len;
@@ -737,6 +800,27 @@ int mc3d_wait(mc3d_ctx *ctx, int slot_idx, mc3d_stats *stats)
         kernel_ms = std::max(kernel_ms, ms);
     }
     if (first_err) return first_err;
+    {   // extrema and column histograms: combined over the devices on the host (a few KB)
+        uint32_t e[4] = {0xffffffffu, 0u, 0xffffffffu, 0u};
+        const mc3d_hist_spec &hs = ctx->done_spec[slot_idx];
+        const size_t n_hist = ctx->done_hist[slot_idx] ? (size_t)hs.n_scat_bins + (size_t)hs.path_bins : 0;
+        std::vector<uint64_t> &counts = ctx->done_counts[slot_idx];
+        counts.assign(n_hist, 0);
+        for (Device &d : ctx->devs) {
+            Slot &s = d.slot[slot_idx];
+            uint32_t de[4];
+            memcpy(de, s.host_extras, sizeof de);
+            de[0] = ~de[0];
+            de[2] = ~de[2];
+            e[0] = std::min(e[0], de[0]); e[1] = std::max(e[1], de[1]);
+            e[2] = std::min(e[2], de[2]); e[3] = std::max(e[3], de[3]);
+            for (size_t k = 0; k < n_hist && 2 + k < s.extras_len; ++k) counts[k] += s.host_extras[2 + k];
+        }
+        mc3d_extrema &x = ctx->done_extrema[slot_idx];
+        if (e[0] > e[1]) { e[0] = e[1] = 0u; e[2] = e[3] = 0u; }   // no photons
+        x.n_scat_min = e[0]; x.n_scat_max = e[1];
+        memcpy(&x.path_min, &e[2], 4); memcpy(&x.path_max, &e[3], 4);
+    }
     Slot &s0 = ctx->devs[0].slot[slot_idx];
     st.n_events = s0.host_tally[s0.tally_len];
     if (s0.user_tally) memcpy(s0.user_tally, s0.host_tally, s0.tally_len * sizeof(uint64_t));
@@ -753,6 +837,41 @@ int mc3d_run(mc3d_ctx *ctx, const mc3d_params *params, const mc3d_ssp_row *table
     int rc = mc3d_run_async(ctx, 0, params, table, n_rows, seed, photon_begin, n_photon, records, tally, stats);
     if (rc) return rc;
     return mc3d_wait(ctx, 0, stats);
+}
+
+int mc3d_set_histograms(mc3d_ctx *ctx, const mc3d_hist_spec *spec)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (!spec) { ctx->hist_on = false; return MC3D_OK; }
+    if (spec->n_scat_bins < 0 || spec->path_bins < 0 || spec->n_scat_bins > (1 << 20) || spec->path_bins > (1 << 20))
+        return fail(MC3D_EINVAL, "histogram bin counts must be in [0, 2^20]");
+    if (spec->n_scat_bins > 0 && !(spec->n_scat_hi > spec->n_scat_lo))
+        return fail(MC3D_EINVAL, "n_scat histogram range must have hi > lo (np.histogram widens an empty range by +-0.5)");
+    if (spec->path_bins > 0 && !(spec->path_hi > spec->path_lo))
+        return fail(MC3D_EINVAL, "path histogram range must have hi > lo (np.histogram widens an empty range by +-0.5)");
+    if (spec->path_bins > 0 && !(spec->path_scale > 0.0)) return fail(MC3D_EINVAL, "path_scale must be positive");
+    ctx->hist_spec = *spec;
+    ctx->hist_on = spec->n_scat_bins > 0 || spec->path_bins > 0;
+    return MC3D_OK;
+}
+
+int mc3d_get_histograms(mc3d_ctx *ctx, int slot_idx, uint64_t *n_scat_counts, uint64_t *path_counts, mc3d_extrema *extrema)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (slot_idx < 0 || slot_idx >= N_SLOTS) return fail(MC3D_EINVAL, "slot must be in [0, %d)", N_SLOTS);
+    if (ctx->devs[0].slot[slot_idx].busy) return fail(MC3D_EINVAL, "slot %d is still in flight; call mc3d_wait first", slot_idx);
+    if (extrema) *extrema = ctx->done_extrema[slot_idx];
+    if (n_scat_counts || path_counts) {
+        if (!ctx->done_hist[slot_idx]) return fail(MC3D_EINVAL, "the last call on slot %d ran without mc3d_set_histograms", slot_idx);
+        const mc3d_hist_spec &hs = ctx->done_spec[slot_idx];
+        const std::vector<uint64_t> &c = ctx->done_counts[slot_idx];
+        if (c.size() != (size_t)hs.n_scat_bins + (size_t)hs.path_bins) return fail(MC3D_EINVAL, "no histogram result on slot %d", slot_idx);
+        if (n_scat_counts && hs.n_scat_bins) memcpy(n_scat_counts, c.data(), hs.n_scat_bins * sizeof(uint64_t));
+        if (path_counts && hs.path_bins) memcpy(path_counts, c.data() + hs.n_scat_bins, hs.path_bins * sizeof(uint64_t));
+    }
+    return MC3D_OK;
 }
 
 int mc3d_reduce_tally(mc3d_ctx *ctx, uint64_t *tally, uint64_t n, int root)

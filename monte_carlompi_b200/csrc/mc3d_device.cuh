@@ -106,6 +106,13 @@ struct FinalizeParams {
     float *path_length;
     unsigned long long *tally;   // [n_rows][N_COND + n_theta_bins * max(1, n_phi_bins)] or null
     unsigned long long *n_events;
+    // optional n_scat / path-length histograms (mc3d_hist_spec) and the always-on extrema
+    uint32_t *extrema;           // [4] ~min n_scat, max n_scat, ~min path, max path (float bits; path >= 0 orders as uint)
+    unsigned long long *hist;    // [n_scat_bins + path_bins] or null
+    const double *hist_edges;    // [n_scat_bins + 1] then [path_bins + 1], np.linspace of the requested ranges
+    int32_t n_scat_bins, path_bins;
+    int32_t hist_smem;           // histogram staged in shared memory behind the tally block
+    double path_scale;
 };
 
 // fp64 replay mode (replay_kernel.cu): per-photon inputs exactly as the reference holds them

@@ -19,7 +19,8 @@ ABI_VERSION = 1
 
 EXPORTS = ('mc3d_abi_version', 'mc3d_last_error', 'mc3d_query', 'mc3d_create', 'mc3d_nccl_unique_id',
            'mc3d_create_rank', 'mc3d_destroy', 'mc3d_host_alloc', 'mc3d_host_free', 'mc3d_run', 'mc3d_run_async',
-           'mc3d_wait', 'mc3d_reduce_tally', 'mc3d_replay', 'mc3d_set_launch', 'mc3d_write_records_text', 'mc3d_py_repr')
+           'mc3d_wait', 'mc3d_reduce_tally', 'mc3d_replay', 'mc3d_set_launch', 'mc3d_write_records_text', 'mc3d_py_repr',
+           'mc3d_set_histograms', 'mc3d_get_histograms')
 
 
 class Mc3dError(RuntimeError):
@@ -59,6 +60,17 @@ class Stats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != 'reserved'}
 
 
+class HistSpec(C.Structure):
+    _fields_ = [('n_scat_bins', C.c_int32), ('path_bins', C.c_int32), ('n_scat_lo', C.c_double),
+                ('n_scat_hi', C.c_double), ('path_lo', C.c_double), ('path_hi', C.c_double),
+                ('path_scale', C.c_double)]
+
+
+class Extrema(C.Structure):
+    _fields_ = [('n_scat_min', C.c_uint32), ('n_scat_max', C.c_uint32), ('path_min', C.c_float),
+                ('path_max', C.c_float)]
+
+
 ROW_DTYPE = np.dtype([('wvl_um', 'f8'), ('ssa_ice', 'f8'), ('ssa_imp', 'f8'), ('g', 'f8'),
                       ('ext_cff_mss', 'f8'), ('p_ext_imp', 'f8')])
 
@@ -96,6 +108,8 @@ def load_library():
     lib.mc3d_write_records_text.restype = C.c_int64
     lib.mc3d_write_records_text.argtypes = [C.c_char_p, i32, u64, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32]
     lib.mc3d_py_repr.argtypes = [C.c_double, C.c_char_p]
+    lib.mc3d_set_histograms.argtypes = [vp, vp]
+    lib.mc3d_get_histograms.argtypes = [vp, i32, vp, vp, vp]
     if lib.mc3d_abi_version() != ABI_VERSION:
         raise Mc3dError('libmc3d.so ABI %d != expected %d' % (lib.mc3d_abi_version(), ABI_VERSION))
     _lib = lib
@@ -245,6 +259,36 @@ class Context(object):
 
     def set_launch(self, blocks_per_sm=0, block_threads=0, refill_threshold=0):
         _check(self._lib.mc3d_set_launch(self._ctx, blocks_per_sm, block_threads, refill_threshold))
+
+    # ---- optional n_scat / path-length histograms (post_processing.py:162-223) --------------------------------
+    def set_histograms(self, n_scat_bins=0, n_scat_range=(0., 1.), path_bins=0, path_range=(0., 1.), path_scale=100.):
+        """Bin n_scat and path_length * path_scale of every later run on the GPU (np.histogram semantics over the
+        given ranges).  ``set_histograms()`` with no bins switches it off."""
+        if not n_scat_bins and not path_bins:
+            self._hist = None
+            _check(self._lib.mc3d_set_histograms(self._ctx, None))
+            return
+        spec = HistSpec(int(n_scat_bins), int(path_bins), float(n_scat_range[0]), float(n_scat_range[1]),
+                        float(path_range[0]), float(path_range[1]), float(path_scale))
+        _check(self._lib.mc3d_set_histograms(self._ctx, C.byref(spec)))
+        self._hist = spec
+
+    def extrema(self, slot=0):
+        """(n_scat_min, n_scat_max, path_min [m], path_max [m]) of the last completed call on ``slot``."""
+        x = Extrema()
+        _check(self._lib.mc3d_get_histograms(self._ctx, slot, None, None, C.byref(x)))
+        return int(x.n_scat_min), int(x.n_scat_max), float(x.path_min), float(x.path_max)
+
+    def histograms(self, slot=0):
+        """(n_scat counts, path counts) of the last completed call on ``slot`` (uint64 arrays; empty when off)."""
+        spec = getattr(self, '_hist', None)
+        if spec is None:
+            raise Mc3dError('set_histograms() was not called')
+        ns = np.zeros(spec.n_scat_bins, np.uint64)
+        pl = np.zeros(spec.path_bins, np.uint64)
+        _check(self._lib.mc3d_get_histograms(self._ctx, slot, _ptr(ns) if ns.size else None,
+                                             _ptr(pl) if pl.size else None, None))
+        return ns, pl
 
     # ---- production mode ------------------------------------------------------------------------------------
     def run_async(self, slot, params, table, seed, photon_begin, n_photon, records=None, tally=None):

@@ -146,13 +146,9 @@ class MonteCarlo(object):
                                 quiet=bool(test))
         return table, k_lo, scale
 
-    # ---- the run (monte_carlo3D.py:1492-1657) -----------------------------------------------------------------
-    def run(self, n_photon, wvl0, half_width, rds_snw, theta_0=0., stokes_params=np.array([1, 0, 0, 0]),
-            shape='sphere', roughness='smooth', test=False, debug=False, Lambertian_surface=False,
-            Lambertian_bottom=True, Lambertian_reflectance=1., seed=None, write_output=True):
-        """ Run the Monte Carlo model given a normal distribution of wavelengths [um].
-            ALL VALUES IN MICRONS
-        """
+    def _setup_case(self, n_photon, wvl0, half_width, rds_snw, theta_0, stokes_params, shape, roughness, test, debug,
+                    Lambertian_surface, Lambertian_bottom, Lambertian_reflectance, seed):
+        """Everything ``run`` does before the photon loop (monte_carlo3D.py:1498-1612): returns (params, table)."""
         if shape != 'sphere':
             raise NotImplementedError('only spheres with the Henyey-Greenstein phase function are built for B200; '
                                       'the aspherical SSP / phase-matrix files are not part of the reference '
@@ -191,6 +187,19 @@ class MonteCarlo(object):
                                     k_first, lambert_bottom=bool(Lambertian_bottom),
                                     lambert_surface=bool(Lambertian_surface), n_theta_bins=int(self.n_theta_bins),
                                     n_phi_bins=int(self.n_phi_bins))
+        return params, table
+
+    # ---- the run (monte_carlo3D.py:1492-1657) -----------------------------------------------------------------
+    def run(self, n_photon, wvl0, half_width, rds_snw, theta_0=0., stokes_params=np.array([1, 0, 0, 0]),
+            shape='sphere', roughness='smooth', test=False, debug=False, Lambertian_surface=False,
+            Lambertian_bottom=True, Lambertian_reflectance=1., seed=None, write_output=True):
+        """ Run the Monte Carlo model given a normal distribution of wavelengths [um].
+            ALL VALUES IN MICRONS
+        """
+        params, table = self._setup_case(n_photon, wvl0, half_width, rds_snw, theta_0, stokes_params, shape, roughness,
+                                         test, debug, Lambertian_surface, Lambertian_bottom, Lambertian_reflectance,
+                                         seed)
+        n_photon = int(n_photon)
         par = self._parallel
         if par is None:
             par = self._parallel = Parallel(n_photon, devices=self.devices)
@@ -298,6 +307,51 @@ class MonteCarlo(object):
         kw.setdefault('seed', seed)
         self.run(c['n_photon'], c['wvl0'], c['half_width'], c['rds_snw'], write_output=write_output, **kw)
         return (self.last_records, self.last_tally, self.last_table)
+
+    # ---- n_scat / path-length histograms without records (post_processing.py:162-223) -------------------------------
+    def histograms(self, n_photon, wvl0, half_width, rds_snw, n_scat_bins=200, path_length_bins=1000, theta_0=0.,
+                   test=False, Lambertian_surface=False, Lambertian_bottom=True, Lambertian_reflectance=1., seed=None):
+        """The two histograms the reference's post-processing draws from the output file --
+        ``np.histogram(n_scat, bins=200)`` and ``np.histogram(path_length * 100, bins=1000)`` [cm], each over the
+        data's own (min, max) -- binned on the GPU(s), so no per-photon record leaves the device: a first pass finds
+        the extrema, a second pass over the same photons (same seed) fills the bins.  Counts equal ``np.histogram``
+        of the records of ``run`` with that seed.  Returns ``{'n_scat': (counts, edges), 'path_length_cm':
+        (counts, edges)}`` on rank 0 (``None`` on the other ranks of a one-process-per-GPU launch)."""
+        params, table = self._setup_case(n_photon, wvl0, half_width, rds_snw, theta_0, np.array([1, 0, 0, 0]), 'sphere',
+                                         'smooth', test, False, Lambertian_surface, Lambertian_bottom,
+                                         Lambertian_reflectance, seed)
+        n_photon = int(n_photon)
+        par = self._parallel
+        if par is None:
+            par = self._parallel = Parallel(n_photon, devices=self.devices)
+        begin, count = par._map(n_photon)
+        ctx = par.open()
+        ctx.set_histograms()
+        ctx.run_async(0, params, table, self.last_seed, begin, count, None, None)
+        ctx.wait(0)
+        ext = np.array(ctx.extrema(0) if count else (2**32 - 1, 0, np.inf, 0.), np.float64)
+        parts = [np.frombuffer(b, np.float64) for b in par.allgather_bytes(ext.tobytes())]
+        ns_lo, ns_hi = min(p[0] for p in parts), max(p[1] for p in parts)
+        pl_lo, pl_hi = min(p[2] for p in parts) * 100., max(p[3] for p in parts) * 100.
+        if ns_lo == ns_hi:                                           # np.histogram's rule for a degenerate range
+            ns_lo, ns_hi = ns_lo - 0.5, ns_hi + 0.5
+        if pl_lo == pl_hi:
+            pl_lo, pl_hi = pl_lo - 0.5, pl_hi + 0.5
+        ctx.set_histograms(n_scat_bins, (ns_lo, ns_hi), path_length_bins, (pl_lo, pl_hi), 100.)
+        try:
+            ctx.run_async(0, params, table, self.last_seed, begin, count, None, None)
+            self.last_stats = ctx.wait(0)
+            ns, pl = ctx.histograms(0)
+        finally:
+            ctx.set_histograms()
+        if par.size > 1:
+            both = np.concatenate([ns, pl])
+            ctx.reduce_tally(both, root=0)
+            ns, pl = both[:len(ns)], both[len(ns):]
+            if par.rank != 0:
+                return None
+        return {'n_scat': (ns, np.linspace(ns_lo, ns_hi, n_scat_bins + 1)),
+                'path_length_cm': (pl, np.linspace(pl_lo, pl_hi, path_length_bins + 1))}
 
     def close(self):
         if self._rec_buf is not None:

@@ -152,6 +152,15 @@ class Parallel(object):
             self._rdzv = None
 
     # ---- gather ----------------------------------------------------------------------------------------------
+    def allgather_bytes(self, blob):
+        """Every rank's ``blob`` on every rank, in rank order (small control data, e.g. histogram extrema)."""
+        if self.size == 1:
+            return [blob]
+        self._call += 1
+        tag = 'allgather%d' % self._call
+        self._rdzv.put('%s.%d' % (tag, self.rank), blob)
+        return [self._rdzv.get('%s.%d' % (tag, r)) for r in range(self.size)]
+
     def answer_and_reduce(self, answer, reduce_work_fn):
         """Reference semantics (parallelize.py:17-26, 40-41): gather every rank's ``answer`` to rank 0 and return
         ``reduce_work_fn(list_of_answers)`` there, ``None`` elsewhere.  ``answer`` is a dict of numpy columns."""

@@ -31,16 +31,19 @@ def test_library_exports_every_declared_symbol():
 def test_header_is_plain_c_and_struct_layouts_match(tmp_path):
     prog = tmp_path / 'layout.c'
     prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "mc3d.h"\nint main(void){'
-                    'printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(mc3d_params), sizeof(mc3d_ssp_row),'
+                    'printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(mc3d_params), sizeof(mc3d_ssp_row),'
                     'sizeof(mc3d_records), sizeof(mc3d_records_f64), sizeof(mc3d_stats),'
-                    'offsetof(mc3d_params, k_first), offsetof(mc3d_params, n_phi_bins), offsetof(mc3d_stats, kernel_ms));'
+                    'offsetof(mc3d_params, k_first), offsetof(mc3d_params, n_phi_bins), offsetof(mc3d_stats, kernel_ms),'
+                    'sizeof(mc3d_hist_spec), offsetof(mc3d_hist_spec, path_scale), sizeof(mc3d_extrema),'
+                    'offsetof(mc3d_extrema, path_min));'
                     'return 0;}\n')
     exe = tmp_path / 'layout'
     subprocess.check_call(['gcc', '-std=c99', '-pedantic', '-Werror', '-I', os.path.join(ROOT, 'include'), str(prog), '-o', str(exe)])
     got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
     want = [C.sizeof(engine.Params), engine.ROW_DTYPE.itemsize, C.sizeof(engine.Records), C.sizeof(engine.RecordsF64),
             C.sizeof(engine.Stats), engine.Params.k_first.offset, engine.Params.n_phi_bins.offset,
-            engine.Stats.kernel_ms.offset]
+            engine.Stats.kernel_ms.offset, C.sizeof(engine.HistSpec), engine.HistSpec.path_scale.offset,
+            C.sizeof(engine.Extrema), engine.Extrema.path_min.offset]
     assert got == want
 
 

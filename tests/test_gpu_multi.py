@@ -63,3 +63,23 @@ def test_one_context_per_gpu_with_nccl_reduce():
     for col in ref:
         assert np.array_equal(np.concatenate([out[r][0][col] for r in range(world)]), ref[col]), col
     assert np.array_equal(out[0][1], tref)
+
+
+def test_histograms_over_two_gpus_equal_one_gpu():
+    _need(2)
+    rows, P = _workload()
+    n, seed = 300001, 9
+    spec = dict(n_scat_bins=200, n_scat_range=(0., 400.), path_bins=1000, path_range=(0., 25.), path_scale=100.)
+    one = gpu_util.context()
+    one.set_histograms(**spec)
+    try:
+        one.run(P, rows, seed, 0, n, records=False, tally=False)
+        want, ext = one.histograms(0), one.extrema(0)
+    finally:
+        one.set_histograms()
+    with engine.Context([0, 1]) as ctx:
+        ctx.set_histograms(**spec)
+        ctx.run(P, rows, seed, 0, n, records=False, tally=False)
+        got = ctx.histograms(0)
+        assert ctx.extrema(0) == ext
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and want[0].sum() > 0
