@@ -10,9 +10,10 @@ What changed underneath: the Python photon loop (monte_carlo3D.py:1613-1616) and
 binding).  Wavelengths are drawn on the GPU from a Philox4x32-10 stream keyed on (seed, photon id), so the
 per-photon SSP arrays of the reference become one small per-wavelength table (ssp.py).
 
-Not carried over (out of scope): aspherical grain shapes / full phase matrices
-(their data files are not part of the reference archive), plotting and debug demos.
-Those raise NotImplementedError rather than silently doing something else.
+Aspherical habits run with the Henyey-Greenstein phase function (``HG=True`` / ``--HG``, same walk, SSPs from the
+habit's ``isca.dat``).  Not carried over (out of scope): the full phase matrix /
+Stokes path (its data files are not part of the reference archive), plotting and debug demos.  Those raise
+NotImplementedError rather than silently doing something else.
 """
 import argparse
 import configparser
@@ -116,8 +117,11 @@ class MonteCarlo(object):
     def setup_output(self, n_photon, wvl0, half_width):
         """ Create output dir for writing data to; returns output_file path
         """
+        shape_dir = 'sphere'
+        if getattr(self, 'shape', 'sphere') != 'sphere':            # monte_carlo3D.py:105-117
+            shape_dir = (self.shape_dir, self.roughness_dir)
         return output.setup_output(self.output_dir, wvl0, half_width, self.snow_effective_radius, n_photon,
-                                   self.theta_0)
+                                   self.theta_0, shape_dir=shape_dir)
 
     # ---- input preparation (monte_carlo3D.py:498-777, 1553-1588) ----------------------------------------------
     def _test_overrides(self):
@@ -136,23 +140,31 @@ class MonteCarlo(object):
             self.__dict__['_preset_' + name] = value
         object.__setattr__(self, name, value)
 
-    def build_table(self, wvl0, half_width, rds_snw, test=False):
-        """Per-wavelength SSP rows covering every wavelength the Gaussian draw can produce (ssp.py)."""
+    def build_table(self, wvl0, half_width, rds_snw, test=False, shape='sphere', roughness='smooth'):
+        """Per-wavelength SSP rows covering every wavelength the Gaussian draw can produce (ssp.py): Mie spheres
+        from the SNICAR NetCDF tables, or -- with ``--HG`` -- an aspherical habit from its ``isca.dat`` library."""
         scale = half_width / 2.355                                  # monte_carlo3D.py:1516
         k_lo, k_hi = ssp.wavelength_grid(wvl0, scale)
-        self.snow_effective_radius = rds_snw                        # monte_carlo3D.py:505
-        table = ssp.build_table(self.optics_dir, self.fi_imp, rds_snw, k_lo, k_hi, self.imp_cnc,
-                                overrides=self._test_overrides() if test else None,
-                                quiet=bool(test))
+        overrides = self._test_overrides() if test else None
+        if shape == 'sphere':
+            self.snow_effective_radius = rds_snw                    # monte_carlo3D.py:505
+            table = ssp.build_table(self.optics_dir, self.fi_imp, rds_snw, k_lo, k_hi, self.imp_cnc,
+                                    overrides=overrides, quiet=bool(test))
+        else:
+            _, self.shape_dir, self.roughness_dir = ssp.aspherical_dirs(shape, roughness, wvl0)
+            table, self.snow_effective_radius = ssp.build_table_aspherical(
+                self.optics_dir, self.fi_imp, shape, roughness, wvl0, rds_snw, k_lo, k_hi, self.imp_cnc, self.rho_ice,
+                overrides=overrides, quiet=bool(test))             # monte_carlo3D.py:1529-1545
         return table, k_lo, scale
 
     def _setup_case(self, n_photon, wvl0, half_width, rds_snw, theta_0, stokes_params, shape, roughness, test, debug,
                     Lambertian_surface, Lambertian_bottom, Lambertian_reflectance, seed):
         """Everything ``run`` does before the photon loop (monte_carlo3D.py:1498-1612): returns (params, table)."""
-        if shape != 'sphere':
-            raise NotImplementedError('only spheres with the Henyey-Greenstein phase function are built for B200; '
-                                      'the aspherical SSP / phase-matrix files are not part of the reference '
-                                      'archive (README.md:40-42)')
+        if shape != 'sphere' and not self.HG:
+            raise NotImplementedError('aspherical shapes are built for B200 with the Henyey-Greenstein phase function '
+                                      'only (MonteCarlo(HG=True) / --HG); the full scattering phase matrix / Stokes '
+                                      'path is out of scope (its data files are not part of the reference archive, '
+                                      'README.md:40-42)')
         if debug:
             raise NotImplementedError('the two-scatter plotting demo (debug=True) is not part of the B200 build')
         if self.phase_functions:
@@ -168,7 +180,8 @@ class MonteCarlo(object):
         self.initial_stokes_params = stokes_params
         n_photon = int(n_photon)
 
-        table, k_first, scale = self.build_table(wvl0, half_width, rds_snw, test=test)
+        table, k_first, scale = self.build_table(wvl0, half_width, rds_snw, test=test, shape=shape,
+                                                 roughness=roughness)
         # same attribute names as the reference, one value per table row instead of per photon
         self.ext_cff_mss = table['ext_cff_mss']
         self.P_ext_imp = table['p_ext_imp']

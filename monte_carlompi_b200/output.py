@@ -38,12 +38,15 @@ def _plain(x):
 
 def setup_output(output_dir, wvl0, half_width, rds_snw, n_photon, theta_0_rad, shape_dir='sphere'):
     """Create <output_dir>/<shape_dir>/ on demand and return a path that does not exist yet (``_N`` de-duplication
-    suffix, monte_carlo3D.py:135-141)."""
+    suffix, monte_carlo3D.py:135-141).  ``shape_dir`` is 'sphere', or a (shape_dir, roughness_dir) pair for the
+    aspherical habits (monte_carlo3D.py:108-117)."""
     if not os.path.isdir(output_dir):
         os.mkdir(output_dir)
-    save_dir = os.path.join(output_dir, shape_dir)
-    if not os.path.isdir(save_dir):
-        os.mkdir(save_dir)
+    save_dir = output_dir
+    for part in ((shape_dir,) if isinstance(shape_dir, str) else tuple(shape_dir)):
+        save_dir = os.path.join(save_dir, part)
+        if not os.path.isdir(save_dir):
+            os.mkdir(save_dir)
     path = os.path.join(save_dir, run_name(wvl0, half_width, rds_snw, n_photon, theta_0_rad))
     i = 0
     while os.path.isfile(path):

@@ -77,6 +77,82 @@ def impurity_file(optics_dir, fi_imp):
     return os.path.join(optics_dir, 'mie', 'snicar', fi_imp)                        # monte_carlo3D.py:666
 
 
+# run(shape=...) / run(roughness=...) -> directory names of the aspherical library (monte_carlo3D.py:185-210)
+SHAPE_DIRS = {'solid hexagonal column': 'solid_column', 'hexagonal plate': 'plate',
+              'hollow hexagonal column': 'hollow_column', 'droxtal': 'droxtal',
+              'hollow bullet rosette': 'hollow_bullet_rosette', 'solid bullet rosette': 'solid_bullet_rosette',
+              '8-element column aggregate': 'column_8elements', '5-element plate aggregate': 'plate_5elements',
+              '10-element plate aggregate': 'plate_10elements'}
+ROUGHNESS_DIRS = {'smooth': 'Rough000', 'moderately rough': 'Rough003', 'severely rough': 'Rough050'}
+
+
+def aspherical_dirs(shape, roughness, wvl0):
+    """(band, shape_dir, roughness_dir) of the aspherical library for a run (monte_carlo3D.py:180-210, 1529-1545)."""
+    if 0.2 <= wvl0 <= 15.25:
+        band = '0.2-15.25'
+    elif 16.4 <= wvl0 <= 99.0:
+        band = '16.4-99.0'
+    else:
+        raise ValueError('wvl0 = %r um is outside the aspherical library (0.2-15.25 and 16.4-99.0 um)' % (wvl0,))
+    if shape not in SHAPE_DIRS:
+        raise ValueError('unknown shape %r; one of %s' % (shape, sorted(SHAPE_DIRS)))
+    if roughness not in ROUGHNESS_DIRS:
+        raise ValueError('unknown roughness %r; one of %s' % (roughness, sorted(ROUGHNESS_DIRS)))
+    return band, SHAPE_DIRS[shape], ROUGHNESS_DIRS[roughness]
+
+
+def read_isca(path):
+    """Columns of ``isca.dat`` (monte_carlo3D.py:216-246): wvl [um], max_dim, volume, G, Q_ext, ssa, asm."""
+    cols = [[] for _ in range(7)]
+    with open(path, 'r') as f:
+        for line in f:
+            parts = line.split()
+            for j in range(7):
+                cols[j].append(float(parts[j]))
+    return [np.array(c) for c in cols]
+
+
+def build_table_aspherical(optics_dir, fi_imp, shape, roughness, wvl0, rds_snw, k_lo, k_hi, imp_cnc, rho_ice,
+                           overrides=None, quiet=False):
+    """SSP rows for aspherical grains under ``--HG`` (get_aspherical_SSPs, monte_carlo3D.py:173-266, 316-336,
+    396-415): the size class whose effective radius RE = 3 V / (4 G) is nearest to ``rds_snw`` at wavelength
+    ``wvl0`` (which must be a wavelength of the library), and for each photon wavelength the NEAREST library
+    wavelength -- no interpolation -- which also replaces the photon's wavelength (monte_carlo3D.py:398-400, 1536),
+    so ``rows['wvl_um']`` holds library wavelengths.  Returns (rows, snow_effective_radius)."""
+    overrides = overrides or {}
+    band, shape_dir, roughness_dir = aspherical_dirs(shape, roughness, wvl0)
+    path = os.path.join(optics_dir, 'ice_optics', band, shape_dir, roughness_dir, 'isca.dat')
+    wvl_in, _, volume_in, G_in, Q_ext_in, ssa_in, asm_in = read_isca(path)
+    wvl0_idxs = np.where(wvl_in == wvl0)                            # monte_carlo3D.py:249
+    if len(wvl0_idxs[0]) == 0:
+        raise ValueError('wvl0 = %r um is not a wavelength of %s (the reference requires an exact member)'
+                         % (wvl0, path))
+    RE = (3. / 4.) * (volume_in / G_in)                             # monte_carlo3D.py:252
+    idx_RE = np.argsort(np.absolute(rds_snw - RE[wvl0_idxs]))[0]
+    snow_effective_radius = RE[wvl0_idxs][idx_RE]
+    valid = np.where(RE == snow_effective_radius)
+    wvl_in, volume_in, G_in, Q_ext_in, ssa_in, asm_in = (a[valid] for a in (wvl_in, volume_in, G_in, Q_ext_in,
+                                                                           ssa_in, asm_in))
+    k = np.arange(k_lo, k_hi + 1)
+    wvls = k / 100.0
+    lib_wvl = np.empty(len(k))
+    vals = {n: np.empty(len(k)) for n in ('ssa_ice', 'ext_cff_mss_ice', 'g')}
+    for j, wvl in enumerate(wvls):
+        i0 = np.argsort(np.absolute(wvl - wvl_in))[0]              # monte_carlo3D.py:331-332
+        lib_wvl[j] = wvl_in[i0]
+        vals['ssa_ice'][j] = ssa_in[i0]
+        vals['ext_cff_mss_ice'][j] = (1e6 * G_in[i0] * Q_ext_in[i0]) / (rho_ice * volume_in[i0])   # :409-412
+        vals['g'][j] = asm_in[i0]
+    imp = read_table(impurity_file(optics_dir, fi_imp), ('wvl', 'ss_alb', 'ext_cff_mss'))
+    imp_v = nearest_pair_interp(imp['wvl'], {'ssa_imp': imp['ss_alb'], 'ext_cff_mss_imp': imp['ext_cff_mss']},
+                                lib_wvl, None if quiet else {})
+    vals.update(imp_v)
+    for name in ('ssa_ice', 'ext_cff_mss_ice', 'g', 'ssa_imp', 'ext_cff_mss_imp'):
+        if name in overrides and overrides[name] is not None:
+            vals[name] = overrides[name] * np.ones(len(k))
+    return derive_rows(lib_wvl, vals, imp_cnc), snow_effective_radius
+
+
 def wavelength_grid(wvl0, sigma, n_sigma=7.0):
     """Integer grid k (wavelength = k / 100 um) covering wvl0 +- n_sigma sigma.
 

@@ -13,6 +13,11 @@ Families:
   * ``const-kat``  ssa 0.9,   g 0.75, ext 16.4        (van de Hulst / Wang 1995 known-answer case)
   * ``const-vis``  ssa 0.999989859099, g 0.89, ext 6.6 (visible, long-tailed walks; monte_carlo3D.py:1872-1878)
   * ``spectral``   smooth analytic lambda dependence scaled with the effective radius
+
+``write_isca`` writes the text table the reference reads for aspherical grains with ``--HG``
+(``<optics_dir>/ice_optics/<band>/<shape>/<roughness>/isca.dat``, seven columns per line: wavelength [um], maximum
+dimension [um], volume [um3], projected area [um2], Q_ext, single-scattering albedo, asymmetry factor;
+monte_carlo3D.py:216-237) -- the Yang et al. (2013) library it points to is not in the archive either.
 """
 import os
 
@@ -81,3 +86,39 @@ def write_optics_dir(optics_dir, kind='spectral', radii_um=(100,), fi_imp='mie_s
     wvl, ssa, ext = impurity_table()
     _write(os.path.join(snicar, fi_imp), {'wvl': wvl, 'ss_alb': ssa, 'ext_cff_mss': ext})
     return optics_dir
+
+
+# (volume / D^3, projected area / D^2) of the synthetic aspherical habits, D = maximum dimension
+_HABIT_GEOMETRY = {'droxtal': (0.30, 0.60), 'solid_column': (0.12, 0.38), 'plate': (0.05, 0.45),
+                   'hollow_column': (0.09, 0.38), 'hollow_bullet_rosette': (0.04, 0.30),
+                   'solid_bullet_rosette': (0.06, 0.30), 'column_8elements': (0.03, 0.22),
+                   'plate_5elements': (0.02, 0.25), 'plate_10elements': (0.015, 0.24)}
+
+ISCA_MAX_DIMS_UM = (2., 5., 10., 20., 50., 100., 200., 400., 700., 1000., 2000., 4000.)
+
+
+def isca_wavelengths_um(far_ir=False):
+    """Two-decimal wavelengths of the synthetic library (so that wvl0 values like 1.3 are table members)."""
+    if far_ir:
+        return np.round(np.arange(16.4, 99.01, 2.0), 2)
+    return np.round(np.concatenate([np.arange(0.2, 3.0, 0.05), np.arange(3.0, 15.26, 0.25)]), 2)
+
+
+def write_isca(optics_dir, shape_dir='droxtal', roughness_dir='Rough000', far_ir=False):
+    """Write a synthetic ``isca.dat`` for one habit / roughness; returns its path."""
+    cv, cg = _HABIT_GEOMETRY[shape_dir]
+    rough = {'Rough000': 0.0, 'Rough003': 0.01, 'Rough050': 0.03}[roughness_dir]
+    band = '16.4-99.0' if far_ir else '0.2-15.25'
+    path = os.path.join(optics_dir, 'ice_optics', band, shape_dir, roughness_dir, 'isca.dat')
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    with open(path, 'w') as f:
+        for w in isca_wavelengths_um(far_ir):
+            coalb100 = np.exp(np.interp(np.log(min(w, 5.0)), np.log(_COALB_ANCHORS_UM), np.log(_COALB_ANCHORS)))
+            for d in ISCA_MAX_DIMS_UM:
+                vol, area = cv * d ** 3, cg * d ** 2
+                r_eff = 0.75 * vol / area
+                ssa = 1.0 - min(coalb100 * r_eff / 100.0, 0.47)
+                q_ext = 2.0 + 0.5 / (1.0 + r_eff / w)
+                g = min(0.97, 0.74 + 0.02 * (w - 1.3) + 0.03 * np.log10(d) - rough)
+                f.write('%8.2f %10.2f %14.6E %14.6E %12.6E %12.6E %12.6E\n' % (w, d, vol, area, q_ext, ssa, g))
+    return path

@@ -127,13 +127,59 @@ def make_text_case(optics_root):
     print('text_default       %s (%d bytes)' % (name, len(text)))
 
 
+# aspherical habit with --HG (monte_carlo3D.py:173-266, 316-336, 396-415, 1529-1545): SSPs from the habit's isca.dat,
+# nearest library wavelength replaces the photon's wavelength
+ASPHERICAL = dict(name='aspherical_hg', n_photon=1500, wvl0=1.3, half_width=0.26, rds_snw=80., theta_0=30., seed=21,
+                  shape='droxtal', roughness='moderately rough', tau_tot=4.0, imp_cnc=1e-6)
+
+
+def make_aspherical_case(optics_root):
+    c = ASPHERICAL
+    optics = os.path.join(optics_root, 'spectral')
+    if not os.path.isdir(os.path.join(optics, 'mie')):
+        ssp_fixtures.write_optics_dir(optics, 'spectral', (50, 100, 250, 500, 1000))
+    ssp_fixtures.write_isca(optics, 'droxtal', 'Rough003')
+    mkw = dict(tau_tot=c['tau_tot'], imp_cnc=c['imp_cnc'], HG=True)
+    rkw = dict(shape=c['shape'], roughness=c['roughness'], Lambertian_bottom=True, Lambertian_reflectance=0.5)
+    r = ref_shim.run_reference(c['n_photon'], c['wvl0'], c['half_width'], c['rds_snw'], c['theta_0'], seed=c['seed'],
+                               optics_dir=optics, model_kwargs=mkw, run_kwargs=rkw, record=True, keep_text=True)
+    drawn, init, stream = regenerate_stream(c['seed'], c['n_photon'], c['wvl0'], c['half_width'], r['offsets'][-1])
+    assert np.array_equal(init, r['init_draws']) and np.array_equal(stream, r['stream'])
+    k = np.rint(drawn * 100).astype(np.int64)
+    uk, first = np.unique(k, return_index=True)
+    rows = np.zeros(len(uk), dtype=[('wvl_um', 'f8'), ('ssa_ice', 'f8'), ('ssa_imp', 'f8'), ('g', 'f8'),
+                                    ('ext_cff_mss', 'f8'), ('p_ext_imp', 'f8')])
+    idx = np.searchsorted(uk, k)
+    for col, src in (('wvl_um', 'wvl'), ('ssa_ice', 'ssa_ice'), ('ssa_imp', 'ssa_imp'), ('g', 'g'),
+                     ('ext_cff_mss', 'ext_cff_mss'), ('p_ext_imp', 'P_ext_imp')):
+        rows[col] = r[src][first]
+        assert np.array_equal(rows[col][idx], r[src]), col          # everything depends on the drawn wavelength only
+    assert np.array_equal(r['wvn'], 1.0 / rows['wvl_um'][idx])
+    cfg = dict(n_photon=c['n_photon'], wvl0=c['wvl0'], half_width=c['half_width'], rds_snw=c['rds_snw'],
+               theta_0=c['theta_0'], seed=c['seed'], fixture='spectral', tau_tot=c['tau_tot'], imp_cnc=c['imp_cnc'],
+               rho_snw=300.0, rho_ice=917.0, Lambertian_bottom=True, Lambertian_surface=False,
+               Lambertian_reflectance=0.5, preset='None', shape=c['shape'], roughness=c['roughness'])
+    name, text = r['text']
+    np.savez_compressed(os.path.join(GOLDEN_DIR, c['name'] + '.npz'), config=np.array(repr(cfg)),
+                        condition=r['condition'].astype(np.int8), wvl_k=k.astype(np.int16), rows_k=uk.astype(np.int16),
+                        theta_n=r['theta_n'], phi_n=r['phi_n'], n_scat=r['n_scat'].astype(np.int32),
+                        path_length=r['path_length'], offsets=r['offsets'], rows=rows, file_name=np.array(name))
+    print('%-18s n=%5d draws=%9d  cond=%s  mean n_scat=%.1f  %s' % (
+        c['name'], c['n_photon'], r['offsets'][-1], np.bincount(r['condition'], minlength=6)[1:].tolist(),
+        r['n_scat'].mean(), name))
+
+
 def main():
     if not ref_shim.reference_available():
         raise SystemExit('reference not present; fixtures can only be regenerated in the build container')
     root = tempfile.mkdtemp(prefix='mc3d_optics_')
     for name in (sys.argv[1:] or CASES):
-        make_case(name, root)
+        if name == ASPHERICAL['name']:
+            make_aspherical_case(root)
+        else:
+            make_case(name, root)
     if not sys.argv[1:]:
+        make_aspherical_case(root)
         make_text_case(root)
 
 

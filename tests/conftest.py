@@ -39,6 +39,9 @@ def optics_root(tmp_path_factory):
     out = {}
     for kind in ('spectral', 'const-kat', 'const-vis', 'const-nir'):
         out[kind] = ssp_fixtures.write_optics_dir(str(root / kind), kind, (50, 100, 250, 500, 1000))
+    # aspherical habits (isca.dat libraries, used with --HG)
+    ssp_fixtures.write_isca(out['spectral'], 'droxtal', 'Rough003')
+    ssp_fixtures.write_isca(out['spectral'], 'solid_column', 'Rough000')
     return out
 
 

@@ -8,7 +8,7 @@ import numpy as np
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 
 CASES = ('c1_default', 'slab_tau3_lb', 'slab_tau05_normal', 'slab_tau3_black', 'impurity', 'kat_vdh', 'vis_debug',
-         'isotropic', 'edge_of_table', 'vis_long', 'lambert_surface', 'c1_full_10k')
+         'isotropic', 'edge_of_table', 'vis_long', 'lambert_surface', 'c1_full_10k', 'aspherical_hg')
 
 
 def regenerate_stream(seed, n_photon, wvl0, half_width, n_walk_draws):
@@ -25,7 +25,10 @@ def load_case(name):
     cfg = ast.literal_eval(str(z['config']))
     rows = z['rows']
     k = z['wvl_k'].astype(np.int64)
-    idx = np.searchsorted(np.rint(rows['wvl_um'] * 100).astype(np.int64), k)
+    # aspherical habits: the drawn wavelength only selects the row; the row's wavelength is the library's nearest one
+    aspherical = 'rows_k' in z.files
+    rows_k = z['rows_k'].astype(np.int64) if aspherical else np.rint(rows['wvl_um'] * 100).astype(np.int64)
+    idx = np.searchsorted(rows_k, k)
     wvls, init, stream = regenerate_stream(cfg['seed'], cfg['n_photon'], cfg['wvl0'], cfg['half_width'],
                                            z['offsets'][-1])
     assert np.array_equal(np.rint(wvls * 100).astype(np.int64), k), 'legacy RandomState stream changed'
@@ -33,7 +36,11 @@ def load_case(name):
                 wvl=wvls, golden={c: z[c] for c in ('condition', 'theta_n', 'phi_n', 'n_scat', 'path_length')})
     for col in ('ssa_ice', 'ssa_imp', 'g', 'ext_cff_mss', 'p_ext_imp'):
         case[col] = rows[col][idx]
-    case['golden']['wvn'] = 1.0 / wvls
+    if aspherical:
+        case['wvl'] = rows['wvl_um'][idx]
+        case['rows_k'] = rows_k
+        case['file_name'] = str(z['file_name'])
+    case['golden']['wvn'] = 1.0 / case['wvl']
     case['golden']['snow_depth'] = cfg['tau_tot'] / (case['ext_cff_mss'] * cfg['rho_snw'])
     return case
 

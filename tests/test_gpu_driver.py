@@ -81,3 +81,38 @@ def test_sweep_equals_case_by_case_runs(run_dir, optics_root, capsys):
         assert os.path.basename(p) == os.path.basename(q)
         assert open(p).read() == open(q).read()
     b.close()
+
+
+def test_aspherical_habit_with_hg(run_dir, optics_root, capsys):
+    # run(shape='droxtal') under --HG: same walk, SSPs from the habit's isca.dat (monte_carlo3D.py:1529-1545), output
+    # under <output_dir>/<shape_dir>/<roughness_dir>/ with the size class' effective radius in the name (:105-131)
+    import golden_util as gu
+    case = gu.load_case('aspherical_hg')
+    cfg = case['cfg']
+    mc = _model(run_dir, optics_root, tau_tot=cfg['tau_tot'], imp_cnc=cfg['imp_cnc'], HG=True, seed=4)
+    n = 400000
+    mc.run(n, cfg['wvl0'], cfg['half_width'], cfg['rds_snw'], theta_0=cfg['theta_0'], shape=cfg['shape'],
+           roughness=cfg['roughness'], Lambertian_bottom=True, Lambertian_reflectance=0.5)
+    path = capsys.readouterr().out.strip().splitlines()[-1]
+    assert path == os.path.join(str(run_dir / 'monte_carlo_results'), 'droxtal', 'Rough003',
+                                '1.3_0.26_75.0_%d_29.999999999999996_HG.txt' % n)
+    assert mc.snow_effective_radius == 75.0
+    # rows == what the reference derived; outcome fractions within 4 sigma of the reference's 1500-photon golden
+    rows_k = case['rows_k']
+    mine = mc.last_table[rows_k - _k_first(mc)]       # table row r <-> drawn wavelength (k_first + r) / 100 um
+    for col in case['rows'].dtype.names:
+        assert np.array_equal(mine[col], case['rows'][col]), col
+    gold = np.bincount(case['golden']['condition'], minlength=6)[1:] / cfg['n_photon']
+    got = np.bincount(mc.last_records['condition'], minlength=6)[1:] / n
+    sigma = np.sqrt(np.maximum(got * (1 - got), 1e-6) / cfg['n_photon'])
+    assert (np.abs(got - gold) < 4 * sigma + 1e-3).all(), (got, gold)
+    # the file's wvn column holds library wavelengths (multiples of 0.05 um), like the reference's
+    first = open(path).read().splitlines()[1:200]
+    wv = np.array([1.0 / float(l.split()[1]) for l in first])
+    assert np.allclose(wv * 20, np.round(wv * 20), atol=1e-9)
+    mc.close()
+
+
+def _k_first(mc):
+    from monte_carlompi_b200 import ssp
+    return ssp.wavelength_grid(mc.wvl0, 0.26 / 2.355)[0]

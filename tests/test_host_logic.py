@@ -28,6 +28,42 @@ def test_ssp_table_matches_reference(optics_root, name, radius, imp_cnc):
     assert ('using nearest value instead' in err.getvalue()) == (name == 'edge_of_table')
 
 
+def test_aspherical_hg_table_matches_reference(optics_root):
+    # get_aspherical_SSPs with --HG (monte_carlo3D.py:173-266, 316-336, 396-415): rows the reference derived, per
+    # drawn wavelength, from the same synthetic isca.dat (oracle/make_golden.py: make_aspherical_case)
+    case = gu.load_case('aspherical_hg')
+    cfg, rows, rows_k = case['cfg'], case['rows'], case['rows_k']
+    full, r_eff = ssp.build_table_aspherical(optics_root['spectral'], 'mie_sot_ChC90_dns_1317.nc', cfg['shape'],
+                                             cfg['roughness'], cfg['wvl0'], cfg['rds_snw'], rows_k.min(), rows_k.max(),
+                                             cfg['imp_cnc'], cfg['rho_ice'], quiet=True)
+    mine = full[rows_k - rows_k.min()]
+    for col in rows.dtype.names:
+        assert np.array_equal(mine[col], rows[col]), col
+    assert r_eff == 75.0                                           # nearest size class to the requested 80 um
+    # wavelengths are replaced by the library's nearest ones (0.05 um steps here), not interpolated
+    assert set(np.round(rows['wvl_um'] * 100).astype(int) % 5) == {0} and len(np.unique(rows['wvl_um'])) < len(rows)
+    # ... and the effective radius of the size class goes into the file name (monte_carlo3D.py:118, 131)
+    name = output.run_name(cfg['wvl0'], cfg['half_width'], r_eff, cfg['n_photon'], np.pi * cfg['theta_0'] / 180.)
+    assert name == case['file_name'] == '1.3_0.26_75.0_1500_29.999999999999996_HG.txt'
+
+
+def test_aspherical_library_errors(optics_root):
+    args = (optics_root['spectral'], 'mie_sot_ChC90_dns_1317.nc')
+    with pytest.raises(ValueError, match='not a wavelength'):      # the reference needs wvl0 to be a library member
+        ssp.build_table_aspherical(*args, 'droxtal', 'moderately rough', 1.31, 80., 120, 140, 0.0, 917.)
+    with pytest.raises(ValueError, match='outside'):
+        ssp.aspherical_dirs('droxtal', 'smooth', 15.8)
+    with pytest.raises(ValueError, match='unknown shape'):
+        ssp.aspherical_dirs('cube', 'smooth', 1.3)
+    assert ssp.aspherical_dirs('8-element column aggregate', 'severely rough', 20.0) == ('16.4-99.0', 'column_8elements', 'Rough050')
+
+
+def test_setup_output_nested_dirs_for_aspherical(tmp_path):
+    p = output.setup_output(str(tmp_path / 'res'), 1.3, 0.085, 75.0, 10, 0.0, shape_dir=('droxtal', 'Rough003'))
+    assert p == os.path.join(str(tmp_path / 'res'), 'droxtal', 'Rough003', '1.3_0.085_75.0_10_0.0_HG.txt')
+    assert os.path.isdir(os.path.dirname(p))
+
+
 def test_ssp_nearest_row_outside_table(optics_root):
     t = ssp.read_table(ssp.ice_file(optics_root['spectral'], 100), ('wvl', 'ss_alb'))
     lo = ssp.nearest_pair_interp(t['wvl'], {'a': t['ss_alb']}, [0.30, 0.305, 0.31, 4.995, 5.0, 9.0])['a']
@@ -188,7 +224,7 @@ def test_drop_in_import_path_and_config(run_dir, monkeypatch):
 def test_out_of_scope_modes_raise(run_dir):
     from monte_carloMPI import monte_carlo3D
     mc = monte_carlo3D.MonteCarlo()
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(NotImplementedError):                       # aspherical without --HG = full phase matrix
         mc.run(10, 1.3, 0.085, 100., shape='droxtal')
     with pytest.raises(NotImplementedError):
         mc.run(10, 1.3, 0.085, 100., debug=True)
