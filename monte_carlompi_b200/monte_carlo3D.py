@@ -246,7 +246,8 @@ class MonteCarlo(object):
         """Run many cases with up to ``engine.N_SLOTS`` of them in flight on the GPU(s).
 
         ``cases``: iterable of dicts with the arguments of ``run`` (``n_photon, wvl0, half_width, rds_snw`` and
-        optionally ``theta_0, Lambertian_bottom, Lambertian_reflectance, Lambertian_surface, test, seed``).  The
+        optionally ``theta_0, Lambertian_bottom, Lambertian_reflectance, Lambertian_surface, test, seed, shape,
+        roughness``).  The
         reference's sweep drivers call ``run`` once per (wavelength, grain size); here each case is enqueued on its
         own slot / CUDA stream, so the long-walk tail, the copy-back and the text formatting of one case overlap
         the walks of the next ones.  Results are identical to calling ``run`` case by case with the same seeds.
@@ -267,13 +268,15 @@ class MonteCarlo(object):
         results = [None] * len(cases)
 
         def finish(slot):
-            k, c, table, tally, n = pending[slot]
+            k, c, table, tally, n, r_eff, dirs = pending[slot]
             stats = ctx.wait(slot)
             rec = {name: col.copy() for name, col in bufs[slot].view(n).items()}
             depth_m = ssp.snow_depth(table, self.tau_tot, self.rho_snw)
             self.last_records, self.last_tally, self.last_table, self.last_stats = rec, tally, table, stats
             if write_output:
-                self.snow_effective_radius = c['rds_snw']
+                self.snow_effective_radius = r_eff
+                self.shape = c.get('shape', 'sphere')
+                self.shape_dir, self.roughness_dir = dirs
                 self.theta_0 = (np.pi * c.get('theta_0', 0.)) / 180.
                 path = self.setup_output(n, c['wvl0'], c['half_width'])
                 output.write_run(path, rec, 1. / table['wvl_um'], depth_m)
@@ -289,7 +292,13 @@ class MonteCarlo(object):
                 if pending[slot] is not None:
                     finish(slot)
                 n = int(c['n_photon'])
-                table, k_first, scale = self.build_table(c['wvl0'], c['half_width'], c['rds_snw'], test=c.get('test', False))
+                shape = c.get('shape', 'sphere')
+                if shape != 'sphere' and not self.HG:
+                    raise NotImplementedError('aspherical shapes need HG=True (see run)')
+                table, k_first, scale = self.build_table(c['wvl0'], c['half_width'], c['rds_snw'], test=c.get('test', False),
+                                                         shape=shape, roughness=c.get('roughness', 'smooth'))
+                r_eff = self.snow_effective_radius
+                dirs = (getattr(self, 'shape_dir', None), getattr(self, 'roughness_dir', None))
                 s = c.get('seed', seed if seed is not None else self.seed)
                 if s is None:
                     s = int.from_bytes(os.urandom(8), 'little')
@@ -300,7 +309,7 @@ class MonteCarlo(object):
                                             n_theta_bins=int(self.n_theta_bins), n_phi_bins=int(self.n_phi_bins))
                 tally = np.zeros((len(table), params.tally_width), np.uint64)
                 ctx.run_async(slot, params, table, int(s), 0, n, bufs[slot], tally)
-                pending[slot] = (k, c, table, tally, n)
+                pending[slot] = (k, c, table, tally, n, r_eff, dirs)
             for slot in sorted(range(depth), key=lambda sl: pending[sl][0] if pending[sl] else -1):
                 if pending[slot] is not None:
                     finish(slot)

@@ -67,12 +67,16 @@ def test_sweep_equals_case_by_case_runs(run_dir, optics_root, capsys):
                                                   (1.55, 0.130, 500, 30.), (0.9, 0.085, 1000, 60.), (2.2, 0.085, 100, 45.),
                                                   (1.0, 0.085, 250, 15.), (1.3, 0.085, 1000, 15.), (1.8, 0.26, 100, 15.),
                                                   (1.3, 1e-12, 100, 15.)])]
-    a = _model(run_dir, optics_root, tau_tot=8.0)
+    # an aspherical habit in the same sweep (needs HG=True): other table loader, other output directory
+    cases.insert(3, dict(n_photon=25000, wvl0=1.55, half_width=0.130, rds_snw=120, theta_0=30., seed=77,
+                         shape='solid hexagonal column', roughness='smooth'))
+    a = _model(run_dir, optics_root, tau_tot=8.0, HG=True)
     a.output_dir = str(run_dir / 'sweep')
     paths = a.run_sweep(cases)
     a.close()
     assert len(paths) == len(cases) and len(set(paths)) == len(cases)
-    b = _model(run_dir, optics_root, tau_tot=8.0)
+    assert os.path.join('sweep', 'solid_column', 'Rough000') in paths[3] and os.path.join('sweep', 'sphere') in paths[4]
+    b = _model(run_dir, optics_root, tau_tot=8.0, HG=True)
     b.output_dir = str(run_dir / 'single')
     for c, p in zip(cases, paths):
         kw = {k: v for k, v in c.items() if k not in ('n_photon', 'wvl0', 'half_width', 'rds_snw')}
