@@ -181,6 +181,7 @@ struct mc3d_ctx {
     int blocks_per_sm = 0;   // 0 = automatic: enough lanes for >= 26 photons each, at most the resident capacity
     int block_threads = 256, refill_threshold = 4;
     int events_per_vote = 0;   // 0 = chosen from the table (see auto_events_per_vote); MC3D_EVENTS_PER_VOTE overrides
+    int drain_give = -1;       // -1 = automatic (16 when other calls are in flight, else off); MC3D_DRAIN_GIVE overrides
     std::chrono::steady_clock::time_point t0[N_SLOTS];
     mc3d_stats pending_stats[N_SLOTS];
     bool hist_on = false;
@@ -331,6 +332,8 @@ static void apply_env(mc3d_ctx *ctx)
 {
     const char *e = getenv("MC3D_EVENTS_PER_VOTE");   // experiments only; results do not depend on it
     if (e && *e) ctx->events_per_vote = atoi(e);
+    e = getenv("MC3D_DRAIN_GIVE");                    // experiments only; results do not depend on it
+    if (e && *e) ctx->drain_give = std::max(0, std::min(31, atoi(e)));
 }
 
 int mc3d_create(mc3d_ctx **out, const int *device_ids, int n_dev)
@@ -547,6 +550,12 @@ static int run_async_impl(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, con
     W.lambert_surface = (P->flags & MC3D_FLAG_LAMBERT_SURFACE) ? 1u : 0u;
     threshold40(P->r_lambert, &W.surf_t_hi, &W.surf_t_lo);
     W.refill_threshold = (uint32_t)ctx->refill_threshold;
+    {   // drain-phase consolidation pays when other launches can use the issue slots it frees, i.e. when other
+        // calls are in flight on this context; a call running alone would only see its tail get longer
+        bool others_busy = false;
+        for (int s = 0; s < N_SLOTS; ++s) others_busy |= (s != slot_idx && ctx->devs[0].slot[s].busy);
+        W.drain_give = ctx->drain_give >= 0 ? (uint32_t)ctx->drain_give : (others_busy ? 16u : 0u);
+    }
 
     ctx->done_hist[slot_idx] = ctx->hist_on;
     ctx->done_spec[slot_idx] = ctx->hist_spec;

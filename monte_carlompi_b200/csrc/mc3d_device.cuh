@@ -77,7 +77,7 @@ struct WalkParams {
     uint32_t refill_threshold;
     uint32_t lambert_surface;   // run(Lambertian_surface=True): the init kernel finishes every photon by itself
     uint32_t surf_t_hi, surf_t_lo;   // 40-bit threshold of the surface reflectance (ssa_event = R, monte_carlo3D.py:1385-1387)
-    uint32_t pad2;
+    uint32_t drain_give;    // drain phase: a warp with <= this many photons hands them to the block's pool (0 = off)
     uint64_t photon_begin;  // global id of photon 0 of this launch
     uint32_t n_photon;      // photons in this launch (< 2^31)
     uint32_t pad;

@@ -17,7 +17,12 @@
 //     monte_carlo3D.py:1232-1237, happen there).  So the divergent part of a refill is a handful of
 //     shared-memory loads, and walk-length divergence is bounded by the threshold instead of by the longest
 //     walk in the warp.  Nothing heavy is inlined next to the event loop: no spills at 48-56 registers.
-//   * when the id range is exhausted the warp drops into a drain loop that resolves lanes immediately.
+//   * when the id range is exhausted the warp drops into a drain loop that resolves lanes immediately.  Draining
+//     warps empty out exponentially (a warp would run ~4 mean walk lengths for its last lane).  When other
+//     launches share the GPU (the host sets P.drain_give then) they consolidate through a small per-block pool in
+//     shared memory: a warp with few photons left hands them (nine words of state each) to the pool and exits,
+//     warps with free lanes take them over, so the issue slots go to the co-resident launches instead of to
+//     mostly-empty warps.  A launch that runs alone skips this: there it would only add latency.
 //   * angles, records and tallies are produced from the raw records by the coalesced finalize kernel
 //     (finalize_kernel.cu).
 //   * per-photon results depend only on (seed, photon id): bit-identical for any grid, block or GPU count.
@@ -32,6 +37,37 @@ struct WarpRing {
     uint4 entry[RING];   // Fresh{pid, row, dtau, pad}
 };
 
+// Photons in flight handed from one draining warp of the block to another (phase B).  The entries and `count` are
+// only touched under `lock`.  `draining` counts the warps currently in phase B: a warp donates only while another
+// one is there to receive, and no warp leaves while the pool holds photons, so nothing is ever stranded.
+constexpr int POOL_CAP = 64;
+constexpr int POOL_WORDS = 9;   // z, ux, uy, uz, path_lo, path_hi, i, plo, row_addr
+struct DrainPool {
+    uint32_t lock, count, draining, pad;
+    uint32_t word[POOL_WORDS][POOL_CAP];
+};
+
+// Pool words are read and written with shared-memory atomics: ordering comes from the lock, but this keeps every
+// cross-warp access explicit (and compute-sanitizer's racecheck, which does not model locks, quiet).
+__device__ __forceinline__ uint32_t pool_get(uint32_t *p) { return atomicOr(p, 0u); }
+__device__ __forceinline__ void pool_put(uint32_t *p, uint32_t v) { atomicExch(p, v); }
+
+// Try-lock: a warp that does not get the pool simply walks on and tries again at its next event.
+__device__ __forceinline__ bool pool_try_acquire(DrainPool &D, uint32_t lane)
+{
+    uint32_t got = 0u;
+    if (lane == 0) got = atomicCAS(&D.lock, 0u, 1u) == 0u ? 1u : 0u;
+    got = __shfl_sync(0xffffffffu, got, 0);
+    if (got) __threadfence_block();
+    return got != 0u;
+}
+__device__ __forceinline__ void pool_release(DrainPool &D, uint32_t lane)
+{
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) atomicExch(&D.lock, 0u);
+}
+
 // EPV = events per lane between two warp votes (1, 2 or 4).  The vote + threshold test costs ~14 issue cycles per
 // iteration; a stopped lane idles < EPV events before it is noticed, so long walks want 4 and strongly absorbing
 // media (a few events per photon) want 1.  Results do not depend on it.
@@ -41,6 +77,8 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) walk_kernel(const __grid_co
     extern __shared__ __align__(16) unsigned char smem_raw[];
     DevRow *rows = reinterpret_cast<DevRow *>(smem_raw);
     WarpRing *rings = reinterpret_cast<WarpRing *>(smem_raw + ((P.n_rows * sizeof(DevRow) + 15) & ~size_t(15)));
+    DrainPool &D = *reinterpret_cast<DrainPool *>(rings + BLOCK / 32);
+    if (threadIdx.x == 0) { D.lock = 0u; D.count = 0u; D.draining = 0u; D.pad = 0u; }
     for (int k = threadIdx.x; k < P.n_rows * (int)(sizeof(DevRow) / 4); k += BLOCK)
         reinterpret_cast<uint32_t *>(rows)[k] = reinterpret_cast<const uint32_t *>(P.rows)[k];
     __syncthreads();
@@ -106,15 +144,71 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) walk_kernel(const __grid_co
 
     // ---- phase B: drain.  Nothing left to hand out; every lane finishes the photon it carries.  The SM empties
     // out, so this loop is latency-bound: it uses the software-pipelined event (next Philox block computed during
-    // the current event's math).
+    // the current event's math).  Warps consolidate through the block's pool (see DrainPool).
     const uint32_t phi = (uint32_t)(P.photon_begin >> 32);
     uint4 wn = philox_event(L.i + 1u, phi, L.pk, P.rk);
+    if (lane == 0) atomicAdd(&D.draining, 1u);
+    // Unlocked peek at the pool (lane 0's view, so every branch on it is warp-uniform), refreshed once per iteration
+    // right before the event so that its latency hides behind the event's math; decisions are re-made under the lock.
+    const uint32_t give_max = P.drain_give;
+    uint32_t peek = 0u;
     for (;;) {
         if (!alive && L.i != 0u) {
             alive = resolve_lane<IMP>(P, rows, rows_addr, L);
             if (alive) wn = philox_event(L.i + 1u, phi, L.pk, P.rk);   // a Lambertian reflection advanced the event count
         }
-        if (__ballot_sync(0xffffffffu, alive) == 0u) break;
+        const uint32_t alive_mask = __ballot_sync(0xffffffffu, alive);
+        const uint32_t n_alive = __popc(alive_mask);
+        if (give_max == 0u) {
+            if (n_alive == 0u) break;
+        } else if (n_alive < 32u) {
+            const bool take = (peek >> 8) != 0u;
+            const bool give = !take && n_alive != 0u && n_alive <= give_max && (peek & 0xffu) > 1u;
+            if ((take || give || n_alive == 0u) && pool_try_acquire(D, lane)) {
+                const uint32_t c = __shfl_sync(0xffffffffu, lane == 0 ? pool_get(&D.count) : 0u, 0);
+                const uint32_t draining = __shfl_sync(0xffffffffu, lane == 0 ? pool_get(&D.draining) : 0u, 0);
+                bool leave = false, taken = false;
+                if (c != 0u) {   // take over photons another warp left behind
+                    const uint32_t k = min(c, 32u - n_alive);
+                    const uint32_t rank = __popc(~alive_mask & ((1u << lane) - 1u));
+                    if (!alive && rank < k) {
+                        const uint32_t e = c - 1u - rank;
+                        L.z = __uint_as_float(pool_get(&D.word[0][e])); L.ux = __uint_as_float(pool_get(&D.word[1][e]));
+                        L.uy = __uint_as_float(pool_get(&D.word[2][e])); L.uz = __uint_as_float(pool_get(&D.word[3][e]));
+                        L.path_lo = __uint_as_float(pool_get(&D.word[4][e]));
+                        L.path_hi = __uint_as_float(pool_get(&D.word[5][e]));
+                        L.i = pool_get(&D.word[6][e]); L.plo = pool_get(&D.word[7][e]); L.row_addr = pool_get(&D.word[8][e]);
+                        taken = true;
+                    }
+                    __syncwarp();
+                    if (lane == 0) pool_put(&D.count, c - k);
+                } else if (n_alive == 0u) {   // nothing carried, nothing waiting: this warp is done
+                    if (lane == 0) atomicSub(&D.draining, 1u);
+                    leave = true;
+                } else if (n_alive <= give_max && draining > 1u && c + n_alive <= (uint32_t)POOL_CAP) {
+                    // hand the photons over to the warps that stay and leave
+                    if (alive) {
+                        const uint32_t e = c + __popc(alive_mask & ((1u << lane) - 1u));
+                        pool_put(&D.word[0][e], __float_as_uint(L.z)); pool_put(&D.word[1][e], __float_as_uint(L.ux));
+                        pool_put(&D.word[2][e], __float_as_uint(L.uy)); pool_put(&D.word[3][e], __float_as_uint(L.uz));
+                        pool_put(&D.word[4][e], __float_as_uint(L.path_lo));
+                        pool_put(&D.word[5][e], __float_as_uint(L.path_hi));
+                        pool_put(&D.word[6][e], L.i); pool_put(&D.word[7][e], L.plo); pool_put(&D.word[8][e], L.row_addr);
+                    }
+                    if (lane == 0) { pool_put(&D.count, c + n_alive); atomicSub(&D.draining, 1u); }
+                    leave = true;
+                }
+                pool_release(D, lane);
+                if (leave) break;
+                if (taken) {   // outside the lock: rebuild the Philox state of the photon just taken over
+                    L.pk = philox_event_constants(L.plo, P.rk);
+                    wn = philox_event(L.i + 1u, phi, L.pk, P.rk);
+                    alive = true;
+                }
+            }
+        }
+        if (give_max != 0u)
+            peek = __shfl_sync(0xffffffffu, lane == 0 ? (pool_get(&D.count) << 8) | min(pool_get(&D.draining), 255u) : 0u, 0);
         if (alive) alive = event_pipelined<IMP>(P, rows, rows_addr, L, wn);
     }
 }
@@ -123,7 +217,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) walk_kernel(const __grid_co
 
 size_t walk_smem_bytes(int n_rows, int block_threads)
 {
-    return ((n_rows * sizeof(DevRow) + 15) & ~size_t(15)) + (block_threads / 32) * sizeof(WarpRing);
+    return ((n_rows * sizeof(DevRow) + 15) & ~size_t(15)) + (block_threads / 32) * sizeof(WarpRing) + sizeof(DrainPool);
 }
 
 template <bool IMP, int EPV, int BLOCK, int MIN_BLOCKS>

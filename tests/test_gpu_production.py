@@ -284,7 +284,7 @@ def test_results_do_not_depend_on_range_split_or_launch_shape():
     P, _ = gpu_util.both_params(15., 6.0, 0.5, 1.3, SIGMA13, 104, True)
     ctx = gpu_util.context()
     n, seed = 300000, 11
-    ref, tref, _ = ctx.run(P, rows, seed, 0, n)
+    ref, tref, st = ctx.run(P, rows, seed, 0, n)
     try:
         # (a) the id range split like 8 ranks (np.array_split), tallies summed: bit-identical to one range
         from monte_carlompi_b200.parallelize import partition
@@ -310,9 +310,22 @@ def test_results_do_not_depend_on_range_split_or_launch_shape():
             for col in ref:
                 assert np.array_equal(rec[col], ref[col]), (col, epv)
             assert np.array_equal(t, tref)
+        # (d) drain-phase consolidation (photons handed between the warps of a block through shared memory; switched
+        #     on automatically when other calls are in flight): any hand-over threshold, several grid shapes
+        for give, bps in (('0', 255), ('8', 255), ('16', 1), ('24', 255), ('31', 2)):
+            os.environ['MC3D_DRAIN_GIVE'] = give
+            try:
+                with engine.Context([0]) as c2:
+                    c2.set_launch(bps, 256, 4)
+                    rec, t, st2 = c2.run(P, rows, seed, 0, n)
+            finally:
+                del os.environ['MC3D_DRAIN_GIVE']
+            for col in ref:
+                assert np.array_equal(rec[col], ref[col]), (col, give)
+            assert np.array_equal(t, tref) and st2['n_events'] == st['n_events']
     finally:
         ctx.set_launch(255, 256, 4)      # back to the automatic grid
-    # (d) a different seed gives a different realisation
+    # (e) a different seed gives a different realisation
     other, _, _ = ctx.run(P, rows, seed + 1, 0, n)
     assert (other['n_scat'] != ref['n_scat']).mean() > 0.5
 
