@@ -278,26 +278,36 @@ def main():
             ctx.reduce_tally(total, root=0)          # the path's single collective: ncclReduce(sum, uint64)
         return events, total
 
+    def timed(n_steps, first_step, with_records):
+        """Barrier + synchronize, CUDA events around exactly n_steps steps, barrier + synchronize; max over ranks.
+        Both events are recorded while every library stream is idle (before the first submission / after the last
+        mc3d_wait returned), so their device timestamps bracket all of the steps' GPU work and copies."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler.active = True
+        t0 = time.perf_counter()
+        e0.record()
+        events, total = pipeline(n_steps, first_step, with_records)
+        checksum = 0
+        if with_records:                                  # read the step's result on the host
+            checksum = int(bufs[0].view(n)['n_scat'][:16].sum()) + int(total[:, 1].sum())
+        e1.record()
+        e1.synchronize()
+        t_dev, t_host = e0.elapsed_time(e1) * 1e-3, time.perf_counter() - t0
+        barrier()
+        sampler.active = False
+        if os.environ.get('MC3D_BENCH_DEBUG'):
+            sys.stderr.write('rank %d: %.4f ms/step (CUDA events), %.4f (host clock)\n'
+                             % (rank, 1e3 * t_dev / n_steps, 1e3 * t_host / n_steps))
+        return max_over_ranks(t_dev), max_over_ranks(t_host), events, total, checksum
+
     # ---- device-resident throughput ("value")
     pipeline(args.warmup, 0, False)
-    barrier()
-    sampler.active = True
-    t0 = time.perf_counter()
-    events_a, total_a = pipeline(args.steps, args.warmup, False)
-    barrier()
-    T_a = max_over_ranks(time.perf_counter() - t0)
-    sampler.active = False
+    T_a, T_a_host, events_a, total_a, _ = timed(args.steps, args.warmup, False)
 
     # ---- end to end through the C ABI with host buffers ("e2e")
     pipeline(args.warmup, args.warmup + args.steps, True)
-    barrier()
-    sampler.active = True
-    t0 = time.perf_counter()
-    events_e, total_e = pipeline(args.steps, 2 * args.warmup + args.steps, True)
-    checksum = int(bufs[0].view(n)['n_scat'][:16].sum()) + int(total_e[:, 1].sum())     # read the result on the host
-    barrier()
-    T_e = max_over_ranks(time.perf_counter() - t0)
-    sampler.active = False
+    T_e, T_e_host, events_e, total_e, checksum = timed(args.steps, 2 * args.warmup + args.steps, True)
 
     # ---- isolated launches: CUDA-event time of walk + finalize per step (no overlap), for the roofline
     iso_ms, iso_events = [], []
@@ -340,7 +350,10 @@ def main():
         line = {
             'metric': 'photon_packets_per_s', 'value': world * args.steps * n / T_a, 'unit': 'photons/s',
             'events_per_s': events_total / T_a, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-            'ms_per_step': 1e3 * T_a / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'ms_per_step': 1e3 * T_a / args.steps, 'host_clock_ms_per_step': 1e3 * T_a_host / args.steps,
+            'timing': 'CUDA events recorded with all library streams idle, around exactly `steps` steps, barrier + synchronize on both '
+                      'sides, max over ranks; host_clock_ms_per_step is the perf_counter cross-check of the same region',
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f32', 'data': 'synthetic',
             'config': workload_config(n, {'events_per_photon': events_a / float(args.steps * n), 'grid_blocks': stats['grid_blocks'],
                                           'block_threads': stats['block_threads'], 'steps_in_flight': depth, 'rank0_numa_node': numa_node}),

@@ -135,27 +135,23 @@ struct DevBuf {
 };
 
 struct Slot {
-    DevBuf<DevRow> rows;
-    DevBuf<double> edges;
-    DevBuf<uint32_t> counters;              // two per chunk: walk-kernel claim counter, length of the fresh list
+    // read-only inputs of a call in one device block (one upload, skipped when nothing changed since the slot's last
+    // call): DevRow[n_rows] | zenith + azimuth edges | column-histogram edges
+    DevBuf<uint8_t> cst;
+    uint8_t *host_cst = nullptr;            // pinned staging
+    size_t host_cst_cap = 0;
+    std::vector<uint8_t> cst_shadow;        // what the device block holds
+    // accumulators in one device block (one memset, one copy back), in 64-bit words:
+    // tally[tally_len] | n_events | extrema (2 words) + column histograms | claim counters (2 x uint32 per chunk)
+    DevBuf<unsigned long long> acc;
+    unsigned long long *host_acc = nullptr; // pinned mirror of tally .. column histograms
+    size_t host_acc_cap = 0, extras_len = 0;
     DevBuf<Fresh> fresh;                    // photons that survived their first event (init kernel -> walk kernel)
     DevBuf<RawResult> raw;
     DevBuf<uint8_t> condition;
     DevBuf<int16_t> wvl_row;
     DevBuf<float> theta_n, phi_n, path_length;
     DevBuf<uint32_t> n_scat;
-    DevBuf<unsigned long long> tally;       // + 1 trailing element: n_events
-    DevBuf<unsigned long long> extras;      // [0..1]: 4 x uint32 extrema, then the optional n_scat / path histograms
-    unsigned long long *host_extras = nullptr;  // pinned mirror
-    size_t host_extras_cap = 0, extras_len = 0;
-    DevBuf<double> hist_edges;
-    double *host_hist_edges = nullptr;
-    size_t host_hist_edges_cap = 0;
-    unsigned long long *host_tally = nullptr;   // pinned mirror of `tally`
-    size_t host_tally_cap = 0;
-    DevRow *host_rows = nullptr;            // pinned staging for the row upload
-    double *host_edges = nullptr;
-    size_t host_rows_cap = 0, host_edges_cap = 0;
     cudaStream_t stream = nullptr;          // each slot has its own stream: two calls in flight overlap on the GPU
     std::vector<cudaEvent_t> ev;            // pairs (begin, end) around walk+finalize of each chunk
     // pending call
@@ -181,6 +177,8 @@ struct mc3d_ctx {
     int blocks_per_sm = 0;   // 0 = automatic: enough lanes for >= 26 photons each, at most the resident capacity
     int block_threads = 256, refill_threshold = 4;
     int events_per_vote = 0;   // 0 = chosen from the table (see auto_events_per_vote); MC3D_EVENTS_PER_VOTE overrides
+    struct Occupancy { bool impurity; int epv, block_threads, bps_variant, n_rows, resident; };
+    std::vector<Occupancy> occupancy;   // resident walk-kernel blocks per SM, queried once per variant
     int drain_give = -1;       // -1 = automatic (16 when other calls are in flight, else off); MC3D_DRAIN_GIVE overrides
     std::chrono::steady_clock::time_point t0[N_SLOTS];
     mc3d_stats pending_stats[N_SLOTS];
@@ -426,14 +424,10 @@ int mc3d_destroy(mc3d_ctx *ctx)
         if (cudaSetDevice(d.id) != cudaSuccess) continue;
         for (Slot &s : d.slot) {
             if (s.stream) cudaStreamSynchronize(s.stream);
-            s.rows.release(); s.edges.release(); s.counters.release(); s.fresh.release(); s.raw.release(); s.condition.release();
-            s.wvl_row.release(); s.theta_n.release(); s.phi_n.release(); s.path_length.release();
-            s.n_scat.release(); s.tally.release(); s.extras.release(); s.hist_edges.release();
-            if (s.host_extras) cudaFreeHost(s.host_extras);
-            if (s.host_hist_edges) cudaFreeHost(s.host_hist_edges);
-            if (s.host_tally) cudaFreeHost(s.host_tally);
-            if (s.host_rows) cudaFreeHost(s.host_rows);
-            if (s.host_edges) cudaFreeHost(s.host_edges);
+            s.cst.release(); s.acc.release(); s.fresh.release(); s.raw.release(); s.condition.release();
+            s.wvl_row.release(); s.theta_n.release(); s.phi_n.release(); s.path_length.release(); s.n_scat.release();
+            if (s.host_cst) cudaFreeHost(s.host_cst);
+            if (s.host_acc) cudaFreeHost(s.host_acc);
             for (cudaEvent_t e : s.ev) cudaEventDestroy(e);
             if (s.stream) cudaStreamDestroy(s.stream);
         }
@@ -588,58 +582,32 @@ static int run_async_impl(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, con
         const uint64_t chunk_cap = std::min<uint64_t>(cnt, CHUNK_PHOTONS);
 
         // ---- buffers
-        CUDA_TRY(s.rows.ensure(n_rows));
-        CUDA_TRY(s.edges.ensure(n_edges));
-        CUDA_TRY(s.counters.ensure(2 * std::max(n_chunks, 1)));
-        CUDA_TRY(s.fresh.ensure(std::max<uint64_t>(chunk_cap, 1)));
-        CUDA_TRY(s.raw.ensure(std::max<uint64_t>(chunk_cap, 1)));
-        CUDA_TRY(s.tally.ensure(tally_len + 1));
-        if (s.host_tally_cap < tally_len + 1) {
-            if (s.host_tally) cudaFreeHost(s.host_tally);
-            s.host_tally = nullptr;
-            CUDA_TRY(cudaHostAlloc((void **)&s.host_tally, (tally_len + 1) * sizeof(unsigned long long), cudaHostAllocPortable));
-            s.host_tally_cap = tally_len + 1;
-        }
-        if (s.host_rows_cap < (size_t)n_rows) {
-            if (s.host_rows) cudaFreeHost(s.host_rows);
-            s.host_rows = nullptr;
-            CUDA_TRY(cudaHostAlloc((void **)&s.host_rows, n_rows * sizeof(DevRow), cudaHostAllocPortable));
-            s.host_rows_cap = n_rows;
-        }
-        if (s.host_edges_cap < n_edges) {
-            if (s.host_edges) cudaFreeHost(s.host_edges);
-            s.host_edges = nullptr;
-            CUDA_TRY(cudaHostAlloc((void **)&s.host_edges, n_edges * sizeof(double), cudaHostAllocPortable));
-            s.host_edges_cap = n_edges;
-        }
         const bool hist_on = ctx->hist_on;
         const mc3d_hist_spec hs = ctx->hist_spec;
         const size_t n_hist = hist_on ? (size_t)hs.n_scat_bins + (size_t)hs.path_bins : 0;
         const size_t n_hist_edges = hist_on ? n_hist + 2 : 0;
+        const size_t rows_bytes = (size_t)n_rows * sizeof(DevRow);
+        const size_t cst_bytes = rows_bytes + (n_edges + n_hist_edges) * sizeof(double);
         s.extras_len = 2 + n_hist;
-        CUDA_TRY(s.extras.ensure(s.extras_len));
-        if (s.host_extras_cap < s.extras_len) {
-            if (s.host_extras) cudaFreeHost(s.host_extras);
-            s.host_extras = nullptr;
-            CUDA_TRY(cudaHostAlloc((void **)&s.host_extras, s.extras_len * sizeof(unsigned long long), cudaHostAllocPortable));
-            s.host_extras_cap = s.extras_len;
+        const size_t acc_copy = tally_len + 1 + s.extras_len;                     // words copied back
+        const size_t acc_words = acc_copy + (size_t)std::max(n_chunks, 1);        // + one word (2 counters) per chunk
+        const bool cst_moved = s.cst.cap < cst_bytes;
+        CUDA_TRY(s.cst.ensure(cst_bytes));
+        CUDA_TRY(s.acc.ensure(acc_words));
+        CUDA_TRY(s.fresh.ensure(std::max<uint64_t>(chunk_cap, 1)));
+        CUDA_TRY(s.raw.ensure(std::max<uint64_t>(chunk_cap, 1)));
+        if (s.host_cst_cap < cst_bytes) {
+            if (s.host_cst) cudaFreeHost(s.host_cst);
+            s.host_cst = nullptr;
+            CUDA_TRY(cudaHostAlloc((void **)&s.host_cst, cst_bytes, cudaHostAllocPortable));
+            s.host_cst_cap = cst_bytes;
         }
-        if (hist_on) {
-            CUDA_TRY(s.hist_edges.ensure(n_hist_edges));
-            if (s.host_hist_edges_cap < n_hist_edges) {
-                if (s.host_hist_edges) cudaFreeHost(s.host_hist_edges);
-                s.host_hist_edges = nullptr;
-                CUDA_TRY(cudaHostAlloc((void **)&s.host_hist_edges, n_hist_edges * sizeof(double), cudaHostAllocPortable));
-                s.host_hist_edges_cap = n_hist_edges;
-            }
-            if (hs.n_scat_bins > 0) linspace_edges(hs.n_scat_lo, hs.n_scat_hi, hs.n_scat_bins, s.host_hist_edges);
-            else s.host_hist_edges[0] = 0.0;
-            if (hs.path_bins > 0) linspace_edges(hs.path_lo, hs.path_hi, hs.path_bins, s.host_hist_edges + hs.n_scat_bins + 1);
-            else s.host_hist_edges[hs.n_scat_bins + 1] = 0.0;
-            CUDA_TRY(cudaMemcpyAsync(s.hist_edges.p, s.host_hist_edges, n_hist_edges * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+        if (s.host_acc_cap < acc_copy) {
+            if (s.host_acc) cudaFreeHost(s.host_acc);
+            s.host_acc = nullptr;
+            CUDA_TRY(cudaHostAlloc((void **)&s.host_acc, acc_copy * sizeof(unsigned long long), cudaHostAllocPortable));
+            s.host_acc_cap = acc_copy;
         }
-        // extrema (the minima are kept complemented, so everything starts at 0) and histogram counts
-        CUDA_TRY(cudaMemsetAsync(s.extras.p, 0, s.extras_len * sizeof(unsigned long long), s.stream));
         const bool want_rec = rec != nullptr;
         if (want_rec && cnt) {
             if (rec->condition) CUDA_TRY(s.condition.ensure(chunk_cap));
@@ -654,27 +622,33 @@ static int run_async_impl(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, con
             CUDA_TRY(cudaEventCreate(&e));
             s.ev.push_back(e);
         }
+        DevRow *d_rows = reinterpret_cast<DevRow *>(s.cst.p);
+        double *d_edges = reinterpret_cast<double *>(s.cst.p + rows_bytes);
+        double *d_hist_edges = d_edges + n_edges;
+        unsigned long long *d_tally = s.acc.p, *d_extras = s.acc.p + tally_len + 1;
+        uint32_t *d_counters = reinterpret_cast<uint32_t *>(s.acc.p + acc_copy);
 
-        // ---- uploads
-        const bool impurity = build_rows(P, table, n_rows, s.host_rows);
-        // np.linspace(0, pi/2, n + 1): start + arange * step with the endpoint forced (numpy/_core/function_base.py)
-        if (P->n_theta_bins > 0) {
-            const double stop = 1.5707963267948966, step = stop / P->n_theta_bins;
-            for (int b = 0; b <= P->n_theta_bins; ++b) s.host_edges[b] = b * step;
-            s.host_edges[P->n_theta_bins] = stop;
-        } else {
-            s.host_edges[0] = 0.0;
+        // ---- inputs: staged in pinned memory, uploaded only when they differ from what the slot's block holds
+        DevRow *h_rows = reinterpret_cast<DevRow *>(s.host_cst);
+        double *h_edges = reinterpret_cast<double *>(s.host_cst + rows_bytes);
+        const bool impurity = build_rows(P, table, n_rows, h_rows);
+        if (P->n_theta_bins > 0) linspace_edges(0.0, 1.5707963267948966, P->n_theta_bins, h_edges);   // np.linspace(0, pi/2, n + 1)
+        else h_edges[0] = 0.0;
+        linspace_edges(0.0, 6.283185307179586, n_phi, h_edges + P->n_theta_bins + 1);               // np.linspace(0, 2 pi, m + 1)
+        if (hist_on) {
+            double *h_hist = h_edges + n_edges;
+            if (hs.n_scat_bins > 0) linspace_edges(hs.n_scat_lo, hs.n_scat_hi, hs.n_scat_bins, h_hist);
+            else h_hist[0] = 0.0;
+            if (hs.path_bins > 0) linspace_edges(hs.path_lo, hs.path_hi, hs.path_bins, h_hist + hs.n_scat_bins + 1);
+            else h_hist[hs.n_scat_bins + 1] = 0.0;
         }
-        {   // azimuth edges np.linspace(0, 2 pi, n_phi + 1), stored after the zenith edges
-            double *pe = s.host_edges + P->n_theta_bins + 1;
-            const double stop = 6.283185307179586, step = stop / n_phi;
-            for (int b = 0; b <= n_phi; ++b) pe[b] = b * step;
-            pe[n_phi] = stop;
+        if (cst_moved || s.cst_shadow.size() != cst_bytes || memcmp(s.cst_shadow.data(), s.host_cst, cst_bytes) != 0) {
+            CUDA_TRY(cudaMemcpyAsync(s.cst.p, s.host_cst, cst_bytes, cudaMemcpyHostToDevice, s.stream));
+            s.cst_shadow.assign(s.host_cst, s.host_cst + cst_bytes);
         }
-        CUDA_TRY(cudaMemcpyAsync(s.rows.p, s.host_rows, n_rows * sizeof(DevRow), cudaMemcpyHostToDevice, s.stream));
-        CUDA_TRY(cudaMemcpyAsync(s.edges.p, s.host_edges, n_edges * sizeof(double), cudaMemcpyHostToDevice, s.stream));
-        CUDA_TRY(cudaMemsetAsync(s.counters.p, 0, 2 * std::max(n_chunks, 1) * sizeof(uint32_t), s.stream));
-        CUDA_TRY(cudaMemsetAsync(s.tally.p, 0, (tally_len + 1) * sizeof(unsigned long long), s.stream));
+        // tallies, event count, extrema (the minima are kept complemented, so everything starts at 0), column
+        // histograms and the claim counters
+        CUDA_TRY(cudaMemsetAsync(s.acc.p, 0, acc_words * sizeof(unsigned long long), s.stream));
 
         // ---- launch configuration: persistent grid, SM count x resident blocks
         // Persistent grid.  A launch ends with a drain phase in which lanes that found no more photons idle while
@@ -684,9 +658,13 @@ static int run_async_impl(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, con
         const int bps_variant = ctx->blocks_per_sm > 0 ? ctx->blocks_per_sm : 1024 / ctx->block_threads;
         const int epv = ctx->events_per_vote > 0 ? ctx->events_per_vote : auto_events_per_vote(P, table, n_rows);
         int resident = 0;
-        {
+        for (const mc3d_ctx::Occupancy &o : ctx->occupancy)
+            if (o.impurity == impurity && o.epv == epv && o.block_threads == ctx->block_threads && o.bps_variant == bps_variant && o.n_rows == n_rows)
+                resident = o.resident;
+        if (resident == 0) {
             WalkParams Wq = W;
             CUDA_TRY(launch_walk(Wq, impurity, epv, ctx->block_threads, bps_variant, 0, s.stream, &resident));
+            if (resident > 0) ctx->occupancy.push_back({impurity, epv, ctx->block_threads, bps_variant, n_rows, resident});
         }
         if (resident < 1) return fail(MC3D_ECUDA, "walk kernel does not fit on an SM (block %d, rows %d)", ctx->block_threads, n_rows);
         resident = std::min(resident, bps_variant);
@@ -703,9 +681,9 @@ static int run_async_impl(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, con
             WalkParams Wc = W;
             Wc.photon_begin = photon_begin + off + c_off;
             Wc.n_photon = c_cnt;
-            Wc.rows = s.rows.p;
-            Wc.counter = s.counters.p + 2 * c;
-            Wc.n_fresh = s.counters.p + 2 * c + 1;
+            Wc.rows = d_rows;
+            Wc.counter = d_counters + 2 * c;
+            Wc.n_fresh = d_counters + 2 * c + 1;
             Wc.fresh = s.fresh.p;
             Wc.raw = s.raw.p;
             const int want = (int)((c_cnt + ctx->block_threads - 1) / ctx->block_threads);
@@ -716,8 +694,8 @@ static int run_async_impl(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, con
             FinalizeParams F;
             memset(&F, 0, sizeof F);
             F.raw = s.raw.p;
-            F.rows = s.rows.p;
-            F.edges = s.edges.p;
+            F.rows = d_rows;
+            F.edges = d_edges;
             F.n_photon = c_cnt;
             F.n_rows = n_rows;
             F.n_theta_bins = P->n_theta_bins;
@@ -730,12 +708,12 @@ static int run_async_impl(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, con
                 F.n_scat = rec->n_scat ? s.n_scat.p : nullptr;
                 F.path_length = rec->path_length ? s.path_length.p : nullptr;
             }
-            F.tally = s.tally.p;
-            F.n_events = s.tally.p + tally_len;
-            F.extrema = reinterpret_cast<uint32_t *>(s.extras.p);
+            F.tally = d_tally;
+            F.n_events = d_tally + tally_len;
+            F.extrema = reinterpret_cast<uint32_t *>(d_extras);
             if (n_hist) {
-                F.hist = s.extras.p + 2;
-                F.hist_edges = s.hist_edges.p;
+                F.hist = d_extras + 2;
+                F.hist_edges = d_hist_edges;
                 F.n_scat_bins = hs.n_scat_bins;
                 F.path_bins = hs.path_bins;
                 F.path_scale = hs.path_scale;
@@ -756,7 +734,8 @@ static int run_async_impl(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, con
 #undef COPY_COL
             }
         }
-        CUDA_TRY(cudaMemcpyAsync(s.host_extras, s.extras.p, s.extras_len * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
+        if (k != 0 || n_dev == 1)   // device 0 of a multi-device context copies after the reduce below
+            CUDA_TRY(cudaMemcpyAsync(s.host_acc, s.acc.p, acc_copy * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
         s.busy = true;
         s.n_photon = cnt;
         s.tally_len = tally_len;
@@ -770,15 +749,15 @@ static int run_async_impl(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, con
         for (int k = 0; k < n_dev; ++k) {
             Device &d = ctx->devs[k];
             Slot &s = d.slot[slot_idx];
-            NCCL_TRY(g_nccl.Reduce(s.tally.p, s.tally.p, tally_len + 1, ncclUint64, ncclSum, 0, ctx->comms[k], s.stream));
+            NCCL_TRY(g_nccl.Reduce(s.acc.p, s.acc.p, tally_len + 1, ncclUint64, ncclSum, 0, ctx->comms[k], s.stream));
         }
         NCCL_TRY(g_nccl.GroupEnd());
     }
-    {
+    if (n_dev > 1) {
         Device &d = ctx->devs[0];
         Slot &s = d.slot[slot_idx];
         CUDA_TRY(cudaSetDevice(d.id));
-        CUDA_TRY(cudaMemcpyAsync(s.host_tally, s.tally.p, (tally_len + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
+        CUDA_TRY(cudaMemcpyAsync(s.host_acc, s.acc.p, (tally_len + 1 + s.extras_len) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
     }
     return MC3D_OK;
 }
@@ -817,13 +796,14 @@ int mc3d_wait(mc3d_ctx *ctx, int slot_idx, mc3d_stats *stats)
         counts.assign(n_hist, 0);
         for (Device &d : ctx->devs) {
             Slot &s = d.slot[slot_idx];
+            const unsigned long long *h_extras = s.host_acc + s.tally_len + 1;
             uint32_t de[4];
-            memcpy(de, s.host_extras, sizeof de);
+            memcpy(de, h_extras, sizeof de);
             de[0] = ~de[0];
             de[2] = ~de[2];
             e[0] = std::min(e[0], de[0]); e[1] = std::max(e[1], de[1]);
             e[2] = std::min(e[2], de[2]); e[3] = std::max(e[3], de[3]);
-            for (size_t k = 0; k < n_hist && 2 + k < s.extras_len; ++k) counts[k] += s.host_extras[2 + k];
+            for (size_t k = 0; k < n_hist && 2 + k < s.extras_len; ++k) counts[k] += h_extras[2 + k];
         }
         mc3d_extrema &x = ctx->done_extrema[slot_idx];
         if (e[0] > e[1]) { e[0] = e[1] = 0u; e[2] = e[3] = 0u; }   // no photons
@@ -831,8 +811,8 @@ int mc3d_wait(mc3d_ctx *ctx, int slot_idx, mc3d_stats *stats)
         memcpy(&x.path_min, &e[2], 4); memcpy(&x.path_max, &e[3], 4);
     }
     Slot &s0 = ctx->devs[0].slot[slot_idx];
-    st.n_events = s0.host_tally[s0.tally_len];
-    if (s0.user_tally) memcpy(s0.user_tally, s0.host_tally, s0.tally_len * sizeof(uint64_t));
+    st.n_events = s0.host_acc[s0.tally_len];
+    if (s0.user_tally) memcpy(s0.user_tally, s0.host_acc, s0.tally_len * sizeof(uint64_t));
     st.kernel_ms = kernel_ms;
     st.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - ctx->t0[slot_idx]).count();
     if (stats) *stats = st;

@@ -225,8 +225,10 @@ static cudaError_t launch_one(const WalkParams &P, int grid, cudaStream_t stream
 {
     const size_t smem = walk_smem_bytes(P.n_rows, BLOCK);
     auto kern = walk_kernel<IMP, EPV, BLOCK, MIN_BLOCKS>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
+    if (smem > 48 * 1024) {   // only large SSP tables need the opt-in (the default table + rings + pool is ~14 KB)
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
     if (occupancy) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occupancy, kern, BLOCK, smem);
     kern<<<grid, BLOCK, smem, stream>>>(P);
     return cudaGetLastError();
