@@ -151,6 +151,12 @@ int mc3d_destroy(mc3d_ctx *ctx);
 int mc3d_host_alloc(void **ptr, uint64_t bytes);
 int mc3d_host_free(void *ptr);
 
+/* Packed layout for the record arrays of an n-photon call: byte offsets of the six mc3d_records columns (in struct
+ * order, each 256-byte aligned) inside one block of *total_bytes.  Optional: when the six host pointers of a
+ * single-device, single-chunk (n <= 2^26) call follow this layout inside one (pinned) block, the library returns the
+ * records with ONE device-to-host copy instead of six; any other arrangement of pointers works as before. */
+int mc3d_records_layout(uint64_t n_photon, uint64_t offsets[6], uint64_t *total_bytes);
+
 /* ---- the hot path --------------------------------------------------------------------------------------
  * Production mode (fp32 walk, Philox4x32-10 keyed on (seed, photon id)).  Walks photon ids
  * [photon_begin, photon_begin + n_photon) -- replaces the loop monte_carlo3D.py:1613-1616 together with

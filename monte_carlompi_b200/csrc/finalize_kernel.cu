@@ -34,7 +34,14 @@ __device__ __forceinline__ int histogram_bin(double x, int n_bins, const double 
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK) finalize_kernel(const __grid_constant__ FinalizeParams P)
 {
-    extern __shared__ unsigned int hist[];   // [n_rows][N_COND + n_theta_bins] when use_smem
+    extern __shared__ unsigned int smem_u32[];
+    float *inv_ext = reinterpret_cast<float *>(smem_u32);   // [n_rows]: metres per unit of path_tau, by SSP row
+    unsigned int *hist = smem_u32 + P.n_rows;               // [n_rows][N_COND + n_theta_bins * n_phi] when use_smem
+    __shared__ unsigned int block_ext[4];                   // extrema of the block (minima complemented)
+    for (int k = threadIdx.x; k < P.n_rows; k += BLOCK) inv_ext[k] = P.rows[k].inv_ext;
+    __shared__ unsigned long long block_events;
+    if (threadIdx.x < 4) block_ext[threadIdx.x] = 0u;
+    if (threadIdx.x == 0) block_events = 0ull;
     const int n_phi = P.n_phi_bins > 1 ? P.n_phi_bins : 1;
     const int stride = N_COND + P.n_theta_bins * n_phi;
     const int hist_len = P.n_rows * stride;
@@ -42,7 +49,7 @@ __global__ void __launch_bounds__(BLOCK) finalize_kernel(const __grid_constant__
     // the optional column histograms sit behind the tally block in shared memory
     const int xh_len = P.hist ? P.n_scat_bins + P.path_bins : 0;
     unsigned int *xh = hist + (tally && P.use_smem ? hist_len : 0);
-    if ((tally && P.use_smem) || (xh_len && P.hist_smem)) {
+    {
         const int len = (tally && P.use_smem ? hist_len : 0) + (P.hist_smem ? xh_len : 0);
         for (int k = threadIdx.x; k < len; k += BLOCK) hist[k] = 0u;
         __syncthreads();
@@ -65,7 +72,7 @@ __global__ void __launch_bounds__(BLOCK) finalize_kernel(const __grid_constant__
         if (P.theta_n) P.theta_n[p] = theta;
         if (P.phi_n) P.phi_n[p] = phi;
         if (P.n_scat) P.n_scat[p] = b.x;
-        const float path_m = a.w * P.rows[row].inv_ext;
+        const float path_m = a.w * inv_ext[row];
         if (P.path_length) P.path_length[p] = path_m;
         events += (unsigned long long)b.x + 1ull;
         ns_min = min(ns_min, b.x);
@@ -107,22 +114,24 @@ __global__ void __launch_bounds__(BLOCK) finalize_kernel(const __grid_constant__
             }
         }
     }
-    // events: warp reduce, one atomic per warp
+    // events: warp reduce, one shared-memory atomic per warp, one global atomic per block (below)
     for (int o = 16; o > 0; o >>= 1) events += __shfl_xor_sync(0xffffffffu, events, o);
-    if ((threadIdx.x & 31) == 0 && events) atomicAdd(P.n_events, events);
-    if (P.extrema) {
+    if ((threadIdx.x & 31) == 0 && events) atomicAdd(&block_events, events);
+    if (P.extrema) {   // warp reduce -> one shared-memory atomic per warp -> one global atomic per block
         ns_min = __reduce_min_sync(0xffffffffu, ns_min);
         ns_max = __reduce_max_sync(0xffffffffu, ns_max);
         pl_min = __reduce_min_sync(0xffffffffu, pl_min);
         pl_max = __reduce_max_sync(0xffffffffu, pl_max);
         if ((threadIdx.x & 31) == 0 && ns_min <= ns_max) {
-            atomicMax(&P.extrema[0], ~ns_min);   // minima are stored complemented: the buffer starts as zeros
-            atomicMax(&P.extrema[1], ns_max);
-            atomicMax(&P.extrema[2], ~pl_min);
-            atomicMax(&P.extrema[3], pl_max);
+            atomicMax(&block_ext[0], ~ns_min);   // minima are stored complemented: the buffer starts as zeros
+            atomicMax(&block_ext[1], ns_max);
+            atomicMax(&block_ext[2], ~pl_min);
+            atomicMax(&block_ext[3], pl_max);
         }
     }
-    if ((tally && P.use_smem) || (xh_len && P.hist_smem)) __syncthreads();
+    __syncthreads();
+    if (P.extrema && threadIdx.x < 4 && block_ext[threadIdx.x] != 0u) atomicMax(&P.extrema[threadIdx.x], block_ext[threadIdx.x]);
+    if (threadIdx.x == 32 % BLOCK && block_events) atomicAdd(P.n_events, block_events);
     if (tally && P.use_smem) {
         for (int k = threadIdx.x; k < hist_len; k += BLOCK) {
             const unsigned int v = hist[k];
@@ -145,7 +154,7 @@ cudaError_t launch_finalize(const FinalizeParams &P, int sm_count, cudaStream_t 
     Q.use_smem = (P.tally != nullptr && hist_bytes <= 96 * 1024) ? 1 : 0;
     const size_t xh_bytes = P.hist ? ((size_t)P.n_scat_bins + (size_t)P.path_bins) * sizeof(unsigned int) : 0;
     Q.hist_smem = (xh_bytes > 0 && xh_bytes <= 64 * 1024) ? 1 : 0;
-    const size_t smem = (Q.use_smem ? hist_bytes : 0) + (Q.hist_smem ? xh_bytes : 0);
+    const size_t smem = (size_t)P.n_rows * sizeof(float) + (Q.use_smem ? hist_bytes : 0) + (Q.hist_smem ? xh_bytes : 0);
     auto kern = finalize_kernel<BLOCK>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -148,10 +148,7 @@ struct Slot {
     size_t host_acc_cap = 0, extras_len = 0;
     DevBuf<Fresh> fresh;                    // photons that survived their first event (init kernel -> walk kernel)
     DevBuf<RawResult> raw;
-    DevBuf<uint8_t> condition;
-    DevBuf<int16_t> wvl_row;
-    DevBuf<float> theta_n, phi_n, path_length;
-    DevBuf<uint32_t> n_scat;
+    DevBuf<uint8_t> recs;                   // record columns of one chunk, packed like mc3d_records_layout
     cudaStream_t stream = nullptr;          // each slot has its own stream: two calls in flight overlap on the GPU
     std::vector<cudaEvent_t> ev;            // pairs (begin, end) around walk+finalize of each chunk
     // pending call
@@ -262,6 +259,18 @@ static void linspace_edges(double start, double stop, int n_bins, double *out)
     const double step = (stop - start) / n_bins;
     for (int b = 0; b <= n_bins; ++b) out[b] = b * step + start;
     out[n_bins] = stop;
+}
+
+// mc3d_records_layout: columns in struct order, each 256-byte aligned
+static const size_t REC_ITEM[6] = {sizeof(uint8_t), sizeof(int16_t), sizeof(float), sizeof(float), sizeof(uint32_t), sizeof(float)};
+static size_t records_layout(uint64_t n, size_t off[6])
+{
+    size_t at = 0;
+    for (int c = 0; c < 6; ++c) {
+        off[c] = at;
+        at += ((size_t)n * REC_ITEM[c] + 255) & ~(size_t)255;
+    }
+    return at;
 }
 
 static void philox_round_keys(uint64_t seed, uint32_t rk[20])
@@ -424,8 +433,7 @@ int mc3d_destroy(mc3d_ctx *ctx)
         if (cudaSetDevice(d.id) != cudaSuccess) continue;
         for (Slot &s : d.slot) {
             if (s.stream) cudaStreamSynchronize(s.stream);
-            s.cst.release(); s.acc.release(); s.fresh.release(); s.raw.release(); s.condition.release();
-            s.wvl_row.release(); s.theta_n.release(); s.phi_n.release(); s.path_length.release(); s.n_scat.release();
+            s.cst.release(); s.acc.release(); s.fresh.release(); s.raw.release(); s.recs.release();
             if (s.host_cst) cudaFreeHost(s.host_cst);
             if (s.host_acc) cudaFreeHost(s.host_acc);
             for (cudaEvent_t e : s.ev) cudaEventDestroy(e);
@@ -448,6 +456,15 @@ int mc3d_host_alloc(void **ptr, uint64_t bytes)
 int mc3d_host_free(void *ptr)
 {
     if (ptr) CUDA_TRY(cudaFreeHost(ptr));
+    return MC3D_OK;
+}
+
+int mc3d_records_layout(uint64_t n_photon, uint64_t offsets[6], uint64_t *total_bytes)
+{
+    if (!offsets || !total_bytes) return fail(MC3D_EINVAL, "null argument");
+    size_t off[6];
+    *total_bytes = records_layout(n_photon, off);
+    for (int c = 0; c < 6; ++c) offsets[c] = off[c];
     return MC3D_OK;
 }
 
@@ -608,14 +625,18 @@ static int run_async_impl(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, con
             CUDA_TRY(cudaHostAlloc((void **)&s.host_acc, acc_copy * sizeof(unsigned long long), cudaHostAllocPortable));
             s.host_acc_cap = acc_copy;
         }
-        const bool want_rec = rec != nullptr;
-        if (want_rec && cnt) {
-            if (rec->condition) CUDA_TRY(s.condition.ensure(chunk_cap));
-            if (rec->wvl_row) CUDA_TRY(s.wvl_row.ensure(chunk_cap));
-            if (rec->theta_n) CUDA_TRY(s.theta_n.ensure(chunk_cap));
-            if (rec->phi_n) CUDA_TRY(s.phi_n.ensure(chunk_cap));
-            if (rec->n_scat) CUDA_TRY(s.n_scat.ensure(chunk_cap));
-            if (rec->path_length) CUDA_TRY(s.path_length.ensure(chunk_cap));
+        const bool want_rec = rec != nullptr && cnt != 0;
+        void *const host_col[6] = {rec ? (void *)rec->condition : nullptr, rec ? (void *)rec->wvl_row : nullptr,
+                                   rec ? (void *)rec->theta_n : nullptr,   rec ? (void *)rec->phi_n : nullptr,
+                                   rec ? (void *)rec->n_scat : nullptr,    rec ? (void *)rec->path_length : nullptr};
+        size_t rec_off[6];
+        if (want_rec) CUDA_TRY(s.recs.ensure(records_layout(chunk_cap, rec_off)));
+        // one copy instead of six when the caller's arrays sit in one block packed like the device's
+        bool packed_host = want_rec && n_dev == 1 && n_chunks == 1;
+        if (packed_host) {
+            records_layout(cnt, rec_off);
+            for (int c = 0; c < 6; ++c)
+                packed_host = packed_host && host_col[c] != nullptr && (uint8_t *)host_col[c] == (uint8_t *)host_col[0] + rec_off[c];
         }
         while ((int)s.ev.size() < 2 * std::max(n_chunks, 1)) {
             cudaEvent_t e;
@@ -701,12 +722,13 @@ static int run_async_impl(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, con
             F.n_theta_bins = P->n_theta_bins;
             F.n_phi_bins = P->n_phi_bins;
             if (want_rec) {
-                F.condition = rec->condition ? s.condition.p : nullptr;
-                F.wvl_row = rec->wvl_row ? s.wvl_row.p : nullptr;
-                F.theta_n = rec->theta_n ? s.theta_n.p : nullptr;
-                F.phi_n = rec->phi_n ? s.phi_n.p : nullptr;
-                F.n_scat = rec->n_scat ? s.n_scat.p : nullptr;
-                F.path_length = rec->path_length ? s.path_length.p : nullptr;
+                records_layout(c_cnt, rec_off);
+                F.condition = host_col[0] ? s.recs.p + rec_off[0] : nullptr;
+                F.wvl_row = host_col[1] ? reinterpret_cast<int16_t *>(s.recs.p + rec_off[1]) : nullptr;
+                F.theta_n = host_col[2] ? reinterpret_cast<float *>(s.recs.p + rec_off[2]) : nullptr;
+                F.phi_n = host_col[3] ? reinterpret_cast<float *>(s.recs.p + rec_off[3]) : nullptr;
+                F.n_scat = host_col[4] ? reinterpret_cast<uint32_t *>(s.recs.p + rec_off[4]) : nullptr;
+                F.path_length = host_col[5] ? reinterpret_cast<float *>(s.recs.p + rec_off[5]) : nullptr;
             }
             F.tally = d_tally;
             F.n_events = d_tally + tally_len;
@@ -720,18 +742,14 @@ static int run_async_impl(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, con
             }
             CUDA_TRY(launch_finalize(F, d.sm_count, s.stream));
             CUDA_TRY(cudaEventRecord(s.ev[2 * c + 1], s.stream));
-            if (want_rec) {
-                const uint64_t o = off + c_off;
-#define COPY_COL(col, T)                                                                                       \
-    if (rec->col)                                                                                              \
-        CUDA_TRY(cudaMemcpyAsync(rec->col + o, s.col.p, (size_t)c_cnt * sizeof(T), cudaMemcpyDeviceToHost, s.stream))
-                COPY_COL(condition, uint8_t);
-                COPY_COL(wvl_row, int16_t);
-                COPY_COL(theta_n, float);
-                COPY_COL(phi_n, float);
-                COPY_COL(n_scat, uint32_t);
-                COPY_COL(path_length, float);
-#undef COPY_COL
+            if (packed_host) {
+                CUDA_TRY(cudaMemcpyAsync(host_col[0], s.recs.p, rec_off[5] + (size_t)c_cnt * REC_ITEM[5], cudaMemcpyDeviceToHost, s.stream));
+            } else if (want_rec) {
+                const uint64_t o = off + c_off;   // this chunk's first photon in the caller's arrays
+                for (int c = 0; c < 6; ++c)
+                    if (host_col[c])
+                        CUDA_TRY(cudaMemcpyAsync((uint8_t *)host_col[c] + o * REC_ITEM[c], s.recs.p + rec_off[c],
+                                                 (size_t)c_cnt * REC_ITEM[c], cudaMemcpyDeviceToHost, s.stream));
             }
         }
         if (k != 0 || n_dev == 1)   // device 0 of a multi-device context copies after the reduce below

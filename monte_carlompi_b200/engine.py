@@ -20,7 +20,7 @@ ABI_VERSION = 1
 EXPORTS = ('mc3d_abi_version', 'mc3d_last_error', 'mc3d_query', 'mc3d_create', 'mc3d_nccl_unique_id',
            'mc3d_create_rank', 'mc3d_destroy', 'mc3d_host_alloc', 'mc3d_host_free', 'mc3d_run', 'mc3d_run_async',
            'mc3d_wait', 'mc3d_reduce_tally', 'mc3d_replay', 'mc3d_set_launch', 'mc3d_write_records_text', 'mc3d_py_repr',
-           'mc3d_set_histograms', 'mc3d_get_histograms')
+           'mc3d_set_histograms', 'mc3d_get_histograms', 'mc3d_records_layout')
 
 
 class Mc3dError(RuntimeError):
@@ -109,6 +109,7 @@ def load_library():
     lib.mc3d_write_records_text.argtypes = [C.c_char_p, i32, u64, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32]
     lib.mc3d_py_repr.argtypes = [C.c_double, C.c_char_p]
     lib.mc3d_set_histograms.argtypes = [vp, vp]
+    lib.mc3d_records_layout.argtypes = [u64, vp, vp]
     lib.mc3d_get_histograms.argtypes = [vp, i32, vp, vp, vp]
     if lib.mc3d_abi_version() != ABI_VERSION:
         raise Mc3dError('libmc3d.so ABI %d != expected %d' % (lib.mc3d_abi_version(), ABI_VERSION))
@@ -202,20 +203,49 @@ class PinnedArray(object):
             pass
 
 
+def records_layout(n):
+    """(byte offsets of the six record columns, total bytes) of the packed block for an n-photon call
+    (mc3d_records_layout): record arrays laid out like this come back with one device-to-host copy."""
+    off = (C.c_uint64 * 6)()
+    total = C.c_uint64(0)
+    _check(load_library().mc3d_records_layout(int(n), off, C.byref(total)))
+    return [int(x) for x in off], int(total.value)
+
+
 class RecordBuffers(object):
-    """One set of pinned SoA record columns for up to ``capacity`` photons."""
+    """Pinned SoA record columns for up to ``capacity`` photons, in one block packed the way the library packs them
+    on the device (so an n-photon call returns its records with a single copy)."""
 
     def __init__(self, capacity):
         self.capacity = int(capacity)
-        self._pinned = {name: PinnedArray(self.capacity, dt) for name, dt in RECORD_COLUMNS}
-        self.struct = Records(*[self._pinned[name].array.ctypes.data for name, _ in RECORD_COLUMNS])
+        _, total = records_layout(self.capacity)
+        self._block = PinnedArray(max(total, 1), np.uint8)
+        self._views = {}
+
+    def _layout(self, n):
+        n = int(n)
+        if n > self.capacity:
+            raise ValueError('%d photons do not fit in RecordBuffers(%d)' % (n, self.capacity))
+        if n not in self._views:
+            off, _ = records_layout(n)
+            base = self._block.array
+            cols = {name: base[o:o + n * np.dtype(dt).itemsize].view(dt) for (name, dt), o in zip(RECORD_COLUMNS, off)}
+            ptrs = Records(*[base.ctypes.data + o for o in off])
+            if len(self._views) > 8:
+                self._views.clear()
+            self._views[n] = (cols, ptrs)
+        return self._views[n]
+
+    def struct_for(self, n):
+        """mc3d_records pointing at the packed columns of an n-photon call."""
+        return self._layout(n)[1]
 
     def view(self, n):
-        return {name: self._pinned[name].array[:n] for name, _ in RECORD_COLUMNS}
+        return dict(self._layout(n)[0])
 
     def free(self):
-        for p in self._pinned.values():
-            p.free()
+        self._views = {}
+        self._block.free()
 
 
 class Context(object):
@@ -297,7 +327,7 @@ class Context(object):
         table = np.ascontiguousarray(table, dtype=ROW_DTYPE)
         rec_struct = None
         if isinstance(records, RecordBuffers):
-            rec_struct = records.struct
+            rec_struct = records.struct_for(n_photon)
         elif records is not None:
             rec_struct = Records(*[records[name].ctypes.data if records.get(name) is not None else None
                                    for name, _ in RECORD_COLUMNS])

@@ -62,3 +62,16 @@ def test_product_package_never_touches_the_oracle():
             if fn.endswith(('.py', '.cu', '.cuh', '.cpp', '.h')):
                 text = open(os.path.join(dirpath, fn)).read()
                 assert 'oracle' not in text.replace('oracle/mc3d_oracle.c, which is how production mode is checked', ''), fn
+
+
+def test_records_layout_is_packed_and_aligned():
+    # host code, no GPU: column offsets of the block that comes back with a single copy
+    off, total = engine.records_layout(1000)
+    assert off == [0, 1024, 3072, 7168, 11264, 15360] and total == 19456
+    off0, total0 = engine.records_layout(0)
+    assert off0 == [0] * 6 and total0 == 0
+    for n in (1, 255, 256, 257, 10**6, 2**26):
+        off, total = engine.records_layout(n)
+        sizes = [n * s for s in (1, 2, 4, 4, 4, 4)]
+        assert all(o % 256 == 0 for o in off) and total % 256 == 0
+        assert all(off[c] + sizes[c] <= off[c + 1] for c in range(5)) and off[5] + sizes[5] <= total
