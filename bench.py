@@ -35,7 +35,7 @@ sys.path.insert(0, ROOT)
 WORKLOAD = dict(wvl0=1.3, half_width=0.085, rds_snw=100, theta_0=15.0, tau_tot=1e6, rho_snw=300.0,
                 lambert_bottom=True, r_lambert=0.5, n_theta_bins=137, fixture='spectral', seed=20190603)
 W_EVENT = 111.0   # algorithmic lane-instructions per scattering event
-NCU_TRAFFIC_BYTES_PER_PHOTON = 47.6   # measured once with ncu (profiles/), see roofline.traffic_is
+NCU_TRAFFIC_BYTES_PER_PHOTON = 47.8   # measured once with ncu (profiles/), see roofline.traffic_is
 LOOP_CEILING_EVENTS_PER_S = 2.11e11   # tools/microbench/hotloop.cu: the event loop alone, all lanes busy, no refill (profiles/)
 
 
@@ -374,7 +374,7 @@ def main():
                                                      'cycles, so 111 lane-instructions cost ~176 cycles (profiles/r01_microbench_hotloop.log)',
                          'traffic': NCU_TRAFFIC_BYTES_PER_PHOTON * n,
                          'traffic_is': 'dram__bytes_read.sum + dram__bytes_write.sum of the walk kernel from the ncu --set full '
-                                       'capture at 1e6 photons per launch (profiles/r01_walk_bench_1e6_ncu_summary.csv: 47.6 MB incl. the 16 MB fresh list), '
+                                       'capture at 1e6 photons per launch (profiles/r01_walk_bench_1e6_ncu_summary.csv: 31.8 MB read + 16.0 MB written, incl. the 16 MB fresh list), '
                                        'scaled per photon; algorithmic bytes of the launch = 16 B/photon fresh-list read + 32 B/photon raw record',
                          'hbm': {'achieved': alg_bytes * n / (np.mean(iso_ms) * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
                                  'frac': alg_bytes * n / (np.mean(iso_ms) * 1e-3) / 1e9 / hbm_peak,
