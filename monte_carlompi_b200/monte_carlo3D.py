@@ -208,6 +208,11 @@ class MonteCarlo(object):
             Lambertian_bottom=True, Lambertian_reflectance=1., seed=None, write_output=True):
         """ Run the Monte Carlo model given a normal distribution of wavelengths [um].
             ALL VALUES IN MICRONS
+
+            write_output: True = the reference's text file (default); 'both' = text plus a binary sidecar
+            <run>.npz (record columns, per-row wvn / snow depth, tallies, SSP table; output.load_run reads either);
+            'binary' = the sidecar only (19 B instead of ~100 B per photon); False = nothing (results stay in
+            self.last_records / self.last_tally).
         """
         params, table = self._setup_case(n_photon, wvl0, half_width, rds_snw, theta_0, stokes_params, shape, roughness,
                                          test, debug, Lambertian_surface, Lambertian_bottom, Lambertian_reflectance,
@@ -238,7 +243,13 @@ class MonteCarlo(object):
         if not write_output:
             return
         output_file = self.setup_output(n_photon, wvl0, half_width)
-        output.write_run(output_file, all_answers, 1. / table['wvl_um'], self.snow_depth)
+        if write_output != 'binary':
+            output.write_run(output_file, all_answers, 1. / table['wvl_um'], self.snow_depth)
+        if write_output in ('both', 'binary'):
+            sidecar = output.write_sidecar(output_file, all_answers, 1. / table['wvl_um'], self.snow_depth, tally=tally,
+                                           table=table)
+            if write_output == 'binary':
+                output_file = sidecar
         print('%s' % output_file)   # for easy post processing
 
     # ---- batched sweeps (reference monte_carlo3D-run.py:60-96, 112-122: one run() per wavelength / grain size) -----

@@ -49,7 +49,7 @@ def setup_output(output_dir, wvl0, half_width, rds_snw, n_photon, theta_0_rad, s
             os.mkdir(save_dir)
     path = os.path.join(save_dir, run_name(wvl0, half_width, rds_snw, n_photon, theta_0_rad))
     i = 0
-    while os.path.isfile(path):
+    while os.path.isfile(path) or os.path.isfile(sidecar_path(path)):   # a binary-only run occupies its name too
         i += 1
         path = os.path.join(save_dir, run_name(wvl0, half_width, rds_snw, n_photon, theta_0_rad, suffix=i))
     return path
@@ -89,3 +89,44 @@ def write_records(path, condition, wvn, theta_n, phi_n, n_scat, path_length, sno
             f.write(format_lines(condition[lo:hi], wvn[lo:hi], theta_n[lo:hi], phi_n[lo:hi], n_scat[lo:hi],
                                  path_length[lo:hi], snow_depth[lo:hi]))
     return path
+
+
+# ---- optional binary sidecar ------------------------------------------------------------
+COLUMNS = ('condition', 'wvn[um^-1]', 'theta_n', 'phi_n', 'n_scat', 'path_length[m],', 'snow_depth[m]')
+
+
+def sidecar_path(path):
+    """<run>.txt -> <run>.npz"""
+    return (path[:-4] if path.endswith('.txt') else path) + '.npz'
+
+
+def write_sidecar(path, records, wvn_by_row, snow_depth_by_row, tally=None, table=None):
+    """Write the run as a compressed-free .npz next to (or instead of) the text file: the compact record columns
+    of libmc3d plus the per-row ``wvn`` / ``snow_depth`` tables (19 bytes per photon instead of ~100 bytes of text),
+    and optionally the GPU tallies and the SSP table.  ``load_run`` gives back exactly what
+    ``pd.read_csv(<run>.txt, delim_whitespace=True)`` (post_processing.py:38) would."""
+    out = sidecar_path(path)
+    extra = {}
+    if tally is not None:
+        extra['tally'] = np.asarray(tally)
+    if table is not None:
+        extra['table'] = np.asarray(table)
+    np.savez(out, wvn_by_row=np.asarray(wvn_by_row, dtype=np.float64),
+             snow_depth_by_row=np.asarray(snow_depth_by_row, dtype=np.float64),
+             **{k: np.asarray(v) for k, v in records.items()}, **extra)
+    return out
+
+
+def load_run(path):
+    """Read a run written by this package -- the reference's text file or the binary sidecar -- into a pandas
+    DataFrame with the reference's column names (note the comma the reference's header carries after
+    ``path_length[m]``).  Both sources give identical frames: float32 columns widen to the doubles the text holds."""
+    import pandas as pd
+    if path.endswith('.npz'):
+        z = np.load(path)
+        rows = z['wvl_row'].astype(np.int64)
+        return pd.DataFrame({'condition': z['condition'].astype(np.int64), 'wvn[um^-1]': z['wvn_by_row'][rows],
+                             'theta_n': z['theta_n'].astype(np.float64), 'phi_n': z['phi_n'].astype(np.float64),
+                             'n_scat': z['n_scat'].astype(np.int64), 'path_length[m],': z['path_length'].astype(np.float64),
+                             'snow_depth[m]': z['snow_depth_by_row'][rows]}, columns=list(COLUMNS))
+    return pd.read_csv(path, sep=r'\s+', float_precision='round_trip')

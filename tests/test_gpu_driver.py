@@ -120,3 +120,21 @@ def test_aspherical_habit_with_hg(run_dir, optics_root, capsys):
 def _k_first(mc):
     from monte_carlompi_b200 import ssp
     return ssp.wavelength_grid(mc.wvl0, 0.26 / 2.355)[0]
+
+
+def test_binary_sidecar_of_a_run(run_dir, optics_root, capsys):
+    from monte_carlompi_b200 import output
+    mc = _model(run_dir, optics_root, seed=8, tau_tot=5.0)
+    mc.run(20000, 1.3, 0.085, 100., theta_0=15., Lambertian_reflectance=0.5, write_output='both')
+    txt = capsys.readouterr().out.strip().splitlines()[-1]
+    a, b = output.load_run(txt), output.load_run(output.sidecar_path(txt))
+    for c in a.columns:
+        assert np.array_equal(a[c].values, b[c].values), c
+    z = np.load(output.sidecar_path(txt))
+    assert np.array_equal(z['tally'], mc.last_tally) and z['tally'][:, 0].sum() == 20000
+    mc.run(20000, 1.3, 0.085, 100., theta_0=15., Lambertian_reflectance=0.5, write_output='binary')
+    npz = capsys.readouterr().out.strip().splitlines()[-1]
+    assert npz.endswith('_HG_1.npz') and not os.path.exists(npz[:-4] + '.txt')      # same de-duplicated run name
+    c = output.load_run(npz)
+    assert np.array_equal(c['n_scat'].values, a['n_scat'].values)
+    mc.close()

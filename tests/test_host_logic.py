@@ -154,6 +154,24 @@ def test_written_file_reads_back_like_post_processing(tmp_path):
     assert np.array_equal(data['wvn[um^-1]'].values, cols['wvn'])
 
 
+def test_binary_sidecar_reads_back_like_the_text_file(tmp_path):
+    pd = pytest.importorskip('pandas')
+    n = 2000
+    rng = np.random.RandomState(1)
+    rec = dict(condition=rng.randint(1, 6, n).astype(np.uint8), wvl_row=rng.randint(0, 53, n).astype(np.int16),
+               theta_n=rng.uniform(0, np.pi, n).astype(np.float32), phi_n=rng.uniform(0, 6.28, n).astype(np.float32),
+               n_scat=rng.randint(0, 5000, n).astype(np.uint32), path_length=rng.exponential(.01, n).astype(np.float32))
+    wvn, depth = 1. / (np.arange(104, 157) / 100.), 1e6 / (np.linspace(16, 17, 53) * 300.)
+    txt = output.write_run(str(tmp_path / 'r.txt'), rec, wvn, depth)
+    npz = output.write_sidecar(txt, rec, wvn, depth, tally=np.zeros((53, 145), np.uint64))
+    assert npz == str(tmp_path / 'r.npz')
+    a, b = output.load_run(txt), output.load_run(npz)
+    assert list(a.columns) == list(b.columns) == list(output.COLUMNS)
+    for c in a.columns:
+        assert a[c].dtype == b[c].dtype and np.array_equal(a[c].values, b[c].values), c
+    assert os.path.getsize(npz) - 53 * 145 * 8 < 0.3 * os.path.getsize(txt)      # 19 B vs ~100 B per photon
+
+
 # ---- partition / ranks (parallelize.py:14-15) -----------------------------------------------------------------
 @pytest.mark.parametrize('n,parts', [(10, 3), (1000000, 8), (7, 8), (0, 4), (33, 1), (10**9, 8)])
 def test_partition_is_array_split(n, parts):
