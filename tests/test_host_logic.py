@@ -199,6 +199,28 @@ def _rdzv_worker(rank, root, q):
     q.put((rank, blob == bytes(range(128))))
 
 
+def _allgather_worker(rank, root, q):
+    par = parallelize.Parallel(100, environ={'RANK': str(rank), 'WORLD_SIZE': '2', 'LOCAL_RANK': str(rank)})
+    par._rdzv = parallelize.FileRendezvous(rank, 2, token='ag', root=root, timeout=30)   # what open() sets up
+    ext = np.array([3. + rank, 40. - rank, 0.5 * (rank + 1), 9. + rank])                  # per-rank extrema
+    parts = [np.frombuffer(b, np.float64) for b in par.allgather_bytes(ext.tobytes())]
+    again = par.allgather_bytes(b'x%d' % rank)                                             # tags do not collide
+    q.put((rank, [p.tolist() for p in parts], again))
+
+
+def test_allgather_bytes_two_processes(tmp_path):
+    # MonteCarlo.histograms combines the per-rank extrema this way (one process per GPU)
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_allgather_worker, args=(r, str(tmp_path), q)) for r in range(2)]
+    [p.start() for p in ps]
+    got = sorted(q.get(timeout=60) for _ in ps)
+    [p.join(30) for p in ps]
+    want = [[3., 40., 0.5, 9.], [4., 39., 1.0, 10.]]
+    assert got == [(0, want, [b'x0', b'x1']), (1, want, [b'x0', b'x1'])]
+    assert parallelize.Parallel(5, environ={}).allgather_bytes(b'solo') == [b'solo']
+
+
 def test_file_rendezvous_two_processes(tmp_path):
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
