@@ -147,8 +147,13 @@ class Parallel(object):
             self.context.close()
             self.context = None
         if self._rdzv is not None:
-            self._rdzv.barrier('close')
-            self._rdzv.cleanup()
+            # every rank checks out; only rank 0 waits (for all of them) and then removes the directory -- nobody
+            # waits on rank 0, so it can never delete a file another rank is still polling for
+            self._rdzv.put('close.%d' % self.rank, b'1')
+            if self.rank == 0:
+                for r in range(1, self.size):
+                    self._rdzv.get('close.%d' % r)
+                self._rdzv.cleanup()
             self._rdzv = None
 
     # ---- gather ----------------------------------------------------------------------------------------------

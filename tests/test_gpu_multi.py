@@ -1,6 +1,7 @@
 """Multi-GPU paths (need >= 2 visible devices; skipped otherwise): one process driving several GPUs with the NCCL
 reduce inside mc3d_run, and one context per GPU (the torchrun layout) with mc3d_reduce_tally.  Results must be
 bit-identical to a single-GPU run: photon results depend only on (seed, photon id), tallies are integers."""
+import os
 import threading
 
 import numpy as np
@@ -83,3 +84,56 @@ def test_histograms_over_two_gpus_equal_one_gpu():
         got = ctx.histograms(0)
         assert ctx.extrema(0) == ext
     assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and want[0].sum() > 0
+
+
+_RANK_SCRIPT = r'''
+import os, sys, shutil, json
+import numpy as np
+root, work, optics = sys.argv[1:4]
+sys.path.insert(0, root)
+os.chdir(work)
+sys.argv = ['monte_carlo3D-run.py']
+from monte_carloMPI import monte_carlo3D
+mc = monte_carlo3D.MonteCarlo(optics_dir=optics, output_dir=os.path.join(work, 'out'), seed=31, tau_tot=6.0)
+mc.run(200001, 1.3, 0.085, 100., theta_0=15., Lambertian_reflectance=0.5)
+h = mc.histograms(200001, 1.3, 0.085, 100., theta_0=15., Lambertian_reflectance=0.5, n_scat_bins=50, path_length_bins=80)
+if h is not None:
+    np.savez(os.path.join(work, 'hist.npz'), ns=h['n_scat'][0], pl=h['path_length_cm'][0], tally=mc.last_tally)
+mc.close()
+'''
+
+
+def test_driver_one_process_per_gpu_equals_one_process(tmp_path, optics_root):
+    # `torchrun --nproc-per-node 2 monte_carlo3D-run.py` layout: every rank runs the script, rank 0 writes the file
+    # (reference: mpirun -np N, README.md:45); ranks find each other through the file rendezvous of parallelize.py
+    _need(2)
+    import shutil
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / 'rank_main.py'
+    script.write_text(_RANK_SCRIPT)
+    outs = {}
+    for world in (1, 2):
+        work = tmp_path / ('w%d' % world)
+        work.mkdir()
+        shutil.copy(os.path.join(root, 'config.ini'), str(work / 'config.ini'))
+        procs = []
+        for rank in range(world):
+            env = dict(os.environ, MC3D_RDZV_DIR=str(work), MASTER_PORT=str(29000 + world))
+            if world > 1:
+                env.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+            else:
+                env.update(CUDA_VISIBLE_DEVICES='0')
+                for k in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK'):
+                    env.pop(k, None)
+            procs.append(subprocess.Popen([sys.executable, str(script), root, str(work), optics_root['spectral']], env=env,
+                                          stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+        res = [p.communicate(timeout=600) for p in procs]
+        assert all(p.returncode == 0 for p in procs), res
+        paths = [l for l in res[0][0].splitlines() if l.endswith('.txt')]
+        assert len(paths) == 1 and all('.txt' not in r[0] for r in res[1:])        # only rank 0 writes / prints
+        outs[world] = (open(paths[0]).read(), np.load(str(work / 'hist.npz')))
+    assert outs[1][0] == outs[2][0]                                                # byte-identical output file
+    for k in ('ns', 'pl', 'tally'):
+        assert np.array_equal(outs[1][1][k], outs[2][1][k]), k

@@ -205,6 +205,12 @@ def _allgather_worker(rank, root, q):
     ext = np.array([3. + rank, 40. - rank, 0.5 * (rank + 1), 9. + rank])                  # per-rank extrema
     parts = [np.frombuffer(b, np.float64) for b in par.allgather_bytes(ext.tobytes())]
     again = par.allgather_bytes(b'x%d' % rank)                                             # tags do not collide
+    if rank == 1:
+        import time
+        time.sleep(1.0)                        # rank 0 reaches close() first and must wait for rank 1, not vice versa
+    t0 = __import__('time').time()
+    par.close()
+    assert __import__('time').time() - t0 < 10.0
     q.put((rank, [p.tolist() for p in parts], again))
 
 
@@ -218,6 +224,7 @@ def test_allgather_bytes_two_processes(tmp_path):
     [p.join(30) for p in ps]
     want = [[3., 40., 0.5, 9.], [4., 39., 1.0, 10.]]
     assert got == [(0, want, [b'x0', b'x1']), (1, want, [b'x0', b'x1'])]
+    assert not [d for d in os.listdir(str(tmp_path)) if d.startswith('mc3d_rdzv_')]       # rank 0 cleaned up after both left
     assert parallelize.Parallel(5, environ={}).allgather_bytes(b'solo') == [b'solo']
 
 
