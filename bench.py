@@ -192,10 +192,12 @@ def main():
     ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--photons', type=int, default=1000000, help='photon packets per step per GPU')
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--inflight', type=int, default=8, help='steps in flight (1..8 library slots)')
+    ap.add_argument('--inflight', type=int, default=16, help='steps in flight (1..16 library slots)')
     ap.add_argument('--launch', default='', help='blocks_per_sm,block_threads,refill_threshold (tuning)')
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
+    if args.impl == 'ours':
+        # at least 3 warm-up steps, and at least one per slot in flight: a slot allocates its device buffers on first use
+        args.warmup = max(args.warmup, 3, min(16, args.inflight))
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))

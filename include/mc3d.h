@@ -45,7 +45,7 @@ extern "C" {
 #define MC3D_COND_DIRECT_TRANSMITTED 3
 #define MC3D_COND_ABSORBED_ICE 4
 #define MC3D_COND_ABSORBED_IMPURITY 5
-#define MC3D_N_SLOTS 8
+#define MC3D_N_SLOTS 16
 #define MC3D_N_COND 8 /* tally stride per wavelength row: index = condition, 0 = total launched, 6..7 unused */
 
 typedef struct mc3d_ctx mc3d_ctx; /* opaque; one per process (or several); not thread-safe per context */
@@ -181,7 +181,7 @@ int mc3d_run(mc3d_ctx *ctx, const mc3d_params *params, const mc3d_ssp_row *table
 
 /* Asynchronous variant: enqueues upload + walk + copy-back on the context's streams and returns; the record
  * and tally buffers must stay valid (and should be pinned) until mc3d_wait.  `slot` (0 .. MC3D_N_SLOTS-1) selects one
- * of eight independent device buffer sets, each with its own stream, so that several calls can be in flight: the
+ * of sixteen independent device buffer sets, each with its own stream, so that several calls can be in flight: the
  * long-walk tail and the copy-back of one call overlap the walks of the next ones.  mc3d_wait(ctx, slot, stats)
  * blocks until that slot is complete. */
 int mc3d_run_async(mc3d_ctx *ctx, int slot, const mc3d_params *params, const mc3d_ssp_row *table, int n_rows,

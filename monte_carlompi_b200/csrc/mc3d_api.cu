@@ -110,7 +110,7 @@ int load_nccl()
 namespace {
 
 constexpr uint64_t CHUNK_PHOTONS = 1ull << 26;   // raw results: 32 B/photon -> 2 GiB per chunk buffer
-constexpr int N_SLOTS = 8;
+constexpr int N_SLOTS = MC3D_N_SLOTS;
 
 template <typename T>
 struct DevBuf {

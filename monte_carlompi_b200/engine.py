@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('MC3D_LIB') or os.path.join(_HERE, 'libmc3d.so')   # MC3D_LIB: A/B-test another build
 
 N_COND = 8
-N_SLOTS = 8
+N_SLOTS = 16
 FLAG_LAMBERT_BOTTOM = 1
 FLAG_LAMBERT_SURFACE = 2
 ABI_VERSION = 1
@@ -324,6 +324,8 @@ class Context(object):
     def run_async(self, slot, params, table, seed, photon_begin, n_photon, records=None, tally=None):
         """Enqueue one walk.  ``records``: RecordBuffers, dict of numpy columns, or None.  ``tally``: uint64 array
         of shape (n_rows, params.tally_width) or None.  Buffers must stay alive until ``wait(slot)``."""
+        if not 0 <= int(slot) < N_SLOTS:
+            raise Mc3dError('slot must be in [0, %d)' % N_SLOTS)
         table = np.ascontiguousarray(table, dtype=ROW_DTYPE)
         rec_struct = None
         if isinstance(records, RecordBuffers):

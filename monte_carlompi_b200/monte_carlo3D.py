@@ -254,7 +254,7 @@ class MonteCarlo(object):
 
     # ---- batched sweeps (reference monte_carlo3D-run.py:60-96, 112-122: one run() per wavelength / grain size) -----
     def run_sweep(self, cases, write_output=True, seed=None):
-        """Run many cases with up to ``engine.N_SLOTS`` of them in flight on the GPU(s).
+        """Run many cases with up to eight of them in flight on the GPU(s).
 
         ``cases``: iterable of dicts with the arguments of ``run`` (``n_photon, wvl0, half_width, rds_snw`` and
         optionally ``theta_0, Lambertian_bottom, Lambertian_reflectance, Lambertian_surface, test, seed, shape,
@@ -272,7 +272,7 @@ class MonteCarlo(object):
         if par.size > 1:
             return [self._run_case_serial(c, write_output, seed) for c in cases]     # one process per GPU: no slots
         ctx = par.open()
-        depth = min(engine.N_SLOTS, len(cases))
+        depth = min(8, engine.N_SLOTS, len(cases))      # each case in flight holds its own pinned record buffers
         n_max = max(int(c['n_photon']) for c in cases)
         bufs = [engine.RecordBuffers(n_max) for _ in range(depth)]
         pending = [None] * depth

@@ -396,3 +396,27 @@ def test_async_slots_overlap_and_match_sync():
         assert np.array_equal(np.concatenate([bufs[0].view(n)[col], bufs[1].view(n)[col]]), ref[col]), col
     assert np.array_equal(tallies[0] + tallies[1], tref) and s0['n_events'] + s1['n_events'] > 2 * n
     [b.free() for b in bufs]
+
+
+def test_every_slot_in_flight_with_ragged_sizes():
+    # all MC3D_N_SLOTS slots busy at once (drain-phase consolidation switches on by itself), different photon counts
+    # per slot, buffers larger than the call: the concatenation equals one synchronous run over the whole id range
+    rows = gpu_util.fixture_table('spectral', 100, 104, 156)
+    P, _ = gpu_util.both_params(15., 6.0, 0.5, 1.3, SIGMA13, 104, True)
+    ctx = gpu_util.context()
+    counts = [30000 + 977 * s for s in range(engine.N_SLOTS)]
+    begins = np.concatenate([[0], np.cumsum(counts)])
+    bufs = [engine.RecordBuffers(max(counts) + 123) for _ in counts]
+    tallies = [np.zeros((len(rows), P.tally_width), np.uint64) for _ in counts]
+    for s, c in enumerate(counts):
+        ctx.run_async(s, P, rows, 21, int(begins[s]), c, bufs[s], tallies[s])
+    with pytest.raises(engine.Mc3dError):
+        ctx.run_async(3, P, rows, 21, 0, 10, bufs[3], tallies[3])           # busy slot
+    with pytest.raises(engine.Mc3dError):
+        ctx.run_async(engine.N_SLOTS, P, rows, 21, 0, 10, None, None)        # no such slot
+    events = sum(ctx.wait(s)['n_events'] for s in range(len(counts)))
+    ref, tref, st = ctx.run(P, rows, 21, 0, int(begins[-1]))
+    for col in ref:
+        assert np.array_equal(np.concatenate([bufs[s].view(c)[col] for s, c in enumerate(counts)]), ref[col]), col
+    assert np.array_equal(sum(tallies), tref) and events == st['n_events']
+    [b.free() for b in bufs]
