@@ -75,3 +75,29 @@ def test_records_layout_is_packed_and_aligned():
         sizes = [n * s for s in (1, 2, 4, 4, 4, 4)]
         assert all(o % 256 == 0 for o in off) and total % 256 == 0
         assert all(off[c] + sizes[c] <= off[c + 1] for c in range(5)) and off[5] + sizes[5] <= total
+
+
+def _build_c_example(tmp_path):
+    exe = tmp_path / 'mc3d_example'
+    subprocess.check_call(['gcc', '-std=c99', '-pedantic', '-Wall', '-Werror', '-I', os.path.join(ROOT, 'include'),
+                           os.path.join(ROOT, 'examples', 'mc3d_example.c'), '-L', os.path.join(ROOT, 'monte_carlompi_b200'),
+                           '-l:libmc3d.so', '-Wl,-rpath,' + os.path.join(ROOT, 'monte_carlompi_b200'), '-lm', '-o', str(exe)])
+    return str(exe)
+
+
+def test_plain_c_program_links_and_fails_loudly_without_a_device(tmp_path):
+    # the boundary is a C ABI: a C99 program binds it with nothing but include/mc3d.h
+    engine.load_library()
+    exe = _build_c_example(tmp_path)
+    if engine.device_count() > 0:
+        pytest.skip('a GPU is visible (the run itself is tests/test_abi.py::test_plain_c_program_known_answer)')
+    r = subprocess.run([exe, '1000'], capture_output=True, text=True)
+    assert r.returncode == 2 and 'no CUDA device' in r.stderr
+
+
+@pytest.mark.gpu
+def test_plain_c_program_known_answer(tmp_path):
+    # van de Hulst / Wang et al. known answer (monte_carlo3D.py:1849-1866) through the C ABI from C
+    r = subprocess.run([_build_c_example(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 0, (r.stdout, r.stderr)
+    assert 'albedo 0.09' in r.stdout
