@@ -307,10 +307,13 @@ def main():
     pipeline(args.warmup, 0, False)
     T_a, T_a_host, events_a, total_a, _ = timed(args.steps, args.warmup, False)
 
-    # ---- end to end through the C ABI with host buffers ("e2e")
+    # ---- end to end through the C ABI with host buffers ("e2e"): every step uploads its inputs (SSP table, bin edges)
+    # from pinned host memory again and copies its records and tallies back
+    ctx.set_input_caching(False)
     pipeline(args.warmup, args.warmup + args.steps, True)
     T_e, T_e_host, events_e, total_e, checksum = timed(args.steps, 2 * args.warmup + args.steps, True)
 
+    ctx.set_input_caching(True)
     # ---- isolated launches: CUDA-event time of walk + finalize per step (no overlap), for the roofline
     iso_ms, iso_events = [], []
     for i in range(min(10, max(3, args.steps))):
@@ -362,7 +365,7 @@ def main():
             'clocks': clocks,
             'e2e': {'value': world * args.steps * n / T_e, 'unit': 'photons/s', 'events_per_s': sum_over_ranks(float(events_e)) / T_e
                     if world == 1 else None, 'ms_per_step': 1e3 * T_e / args.steps,
-                    'h2d_bytes_per_step': int(rows.nbytes + 8 * (P.n_theta_bins + 1)),
+                    'h2d_bytes_per_step': int(64 * n_rows + 8 * (P.n_theta_bins + 1 + max(1, P.n_phi_bins) + 1)),   # DevRow table + bin edges
                     'd2h_bytes_per_step': int(19 * n + tallies[0].nbytes + 8), 'host_checksum': checksum},
             'gpu_launches': 3 * args.steps * world,   # init + walk + finalize kernels per step and rank
             'roofline': {'bound': 'issue', 'unit': 'events/s', 'achieved': ach, 'peak': peak, 'frac': ach / peak,

@@ -230,6 +230,10 @@ int mc3d_py_repr(double x, char *buf);
  * number of waiting lanes at which a warp resolves / refills (default 4).  0 keeps the current value. */
 int mc3d_set_launch(mc3d_ctx *ctx, int blocks_per_sm, int block_threads, int refill_threshold);
 
+/* Input caching (default on): a call whose SSP table, bin edges and histogram edges equal what its slot uploaded
+ * last time skips the host-to-device copy (a few KB).  enabled = 0 makes every call upload its inputs again. */
+int mc3d_set_input_caching(mc3d_ctx *ctx, int enabled);
+
 #ifdef __cplusplus
 }
 #endif

@@ -176,6 +176,7 @@ struct mc3d_ctx {
     int events_per_vote = 0;   // 0 = chosen from the table (see auto_events_per_vote); MC3D_EVENTS_PER_VOTE overrides
     struct Occupancy { bool impurity; int epv, block_threads, bps_variant, n_rows, resident; };
     std::vector<Occupancy> occupancy;   // resident walk-kernel blocks per SM, queried once per variant
+    bool input_caching = true; // skip the upload of inputs identical to the slot's previous call
     int drain_give = -1;       // -1 = automatic (16 when other calls are in flight, else off); MC3D_DRAIN_GIVE overrides
     std::chrono::steady_clock::time_point t0[N_SLOTS];
     mc3d_stats pending_stats[N_SLOTS];
@@ -459,6 +460,14 @@ int mc3d_host_free(void *ptr)
     return MC3D_OK;
 }
 
+int mc3d_set_input_caching(mc3d_ctx *ctx, int enabled)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    ctx->input_caching = enabled != 0;
+    return MC3D_OK;
+}
+
 int mc3d_records_layout(uint64_t n_photon, uint64_t offsets[6], uint64_t *total_bytes)
 {
     if (!offsets || !total_bytes) return fail(MC3D_EINVAL, "null argument");
@@ -663,7 +672,7 @@ static int run_async_impl(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, con
             if (hs.path_bins > 0) linspace_edges(hs.path_lo, hs.path_hi, hs.path_bins, h_hist + hs.n_scat_bins + 1);
             else h_hist[hs.n_scat_bins + 1] = 0.0;
         }
-        if (cst_moved || s.cst_shadow.size() != cst_bytes || memcmp(s.cst_shadow.data(), s.host_cst, cst_bytes) != 0) {
+        if (!ctx->input_caching || cst_moved || s.cst_shadow.size() != cst_bytes || memcmp(s.cst_shadow.data(), s.host_cst, cst_bytes) != 0) {
             CUDA_TRY(cudaMemcpyAsync(s.cst.p, s.host_cst, cst_bytes, cudaMemcpyHostToDevice, s.stream));
             s.cst_shadow.assign(s.host_cst, s.host_cst + cst_bytes);
         }

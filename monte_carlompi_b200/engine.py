@@ -20,7 +20,7 @@ ABI_VERSION = 1
 EXPORTS = ('mc3d_abi_version', 'mc3d_last_error', 'mc3d_query', 'mc3d_create', 'mc3d_nccl_unique_id',
            'mc3d_create_rank', 'mc3d_destroy', 'mc3d_host_alloc', 'mc3d_host_free', 'mc3d_run', 'mc3d_run_async',
            'mc3d_wait', 'mc3d_reduce_tally', 'mc3d_replay', 'mc3d_set_launch', 'mc3d_write_records_text', 'mc3d_py_repr',
-           'mc3d_set_histograms', 'mc3d_get_histograms', 'mc3d_records_layout')
+           'mc3d_set_histograms', 'mc3d_get_histograms', 'mc3d_records_layout', 'mc3d_set_input_caching')
 
 
 class Mc3dError(RuntimeError):
@@ -110,6 +110,7 @@ def load_library():
     lib.mc3d_py_repr.argtypes = [C.c_double, C.c_char_p]
     lib.mc3d_set_histograms.argtypes = [vp, vp]
     lib.mc3d_records_layout.argtypes = [u64, vp, vp]
+    lib.mc3d_set_input_caching.argtypes = [vp, i32]
     lib.mc3d_get_histograms.argtypes = [vp, i32, vp, vp, vp]
     if lib.mc3d_abi_version() != ABI_VERSION:
         raise Mc3dError('libmc3d.so ABI %d != expected %d' % (lib.mc3d_abi_version(), ABI_VERSION))
@@ -286,6 +287,10 @@ class Context(object):
 
     def __exit__(self, *exc):
         self.close()
+
+    def set_input_caching(self, enabled=True):
+        """Skip (default) or force the upload of inputs identical to the slot's previous call."""
+        _check(self._lib.mc3d_set_input_caching(self._ctx, 1 if enabled else 0))
 
     def set_launch(self, blocks_per_sm=0, block_threads=0, refill_threshold=0):
         _check(self._lib.mc3d_set_launch(self._ctx, blocks_per_sm, block_threads, refill_threshold))

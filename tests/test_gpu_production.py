@@ -419,4 +419,17 @@ def test_every_slot_in_flight_with_ragged_sizes():
     for col in ref:
         assert np.array_equal(np.concatenate([bufs[s].view(c)[col] for s, c in enumerate(counts)]), ref[col]), col
     assert np.array_equal(sum(tallies), tref) and events == st['n_events']
+    # input caching off (every call uploads its table again) and a table that changes between calls on one slot
+    ctx.set_input_caching(False)
+    try:
+        again, tagain, _ = ctx.run(P, rows, 21, 0, counts[0])
+    finally:
+        ctx.set_input_caching(True)
+    assert np.array_equal(again['n_scat'], ref['n_scat'][:counts[0]])
+    rows2 = rows.copy()
+    rows2['ssa_ice'] = 0.5
+    dark, _, _ = ctx.run(P, rows2, 21, 0, counts[0])
+    assert dark['n_scat'].mean() < 0.2 * again['n_scat'].mean()                # the new table was uploaded, not the cached one
+    back, _, _ = ctx.run(P, rows, 21, 0, counts[0])
+    assert np.array_equal(back['n_scat'], again['n_scat'])
     [b.free() for b in bufs]
