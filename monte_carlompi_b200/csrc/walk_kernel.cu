@@ -148,9 +148,9 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) walk_kernel(const __grid_co
     const uint32_t phi = (uint32_t)(P.photon_begin >> 32);
     uint4 wn = philox_event(L.i + 1u, phi, L.pk, P.rk);
     if (lane == 0) atomicAdd(&D.draining, 1u);
-    // Unlocked peek at the pool (lane 0's view, so every branch on it is warp-uniform), refreshed once per iteration
-    // right before the event so that its latency hides behind the event's math; decisions are re-made under the lock.
-    const uint32_t give_max = P.drain_give;
+    const uint32_t give_max = P.drain_give;   // 0: plain drain loop (the launch runs alone)
+    // Unlocked peek at the pool: (count << 8) | draining, lane 0's view, so every branch on it is warp-uniform.
+    // Refreshed once per iteration, one event stale; every decision is re-made under the lock.
     uint32_t peek = 0u;
     for (;;) {
         if (!alive && L.i != 0u) {
