@@ -9,8 +9,10 @@ lie, runs ``MonteCarlo.run`` with a seeded ``np.random`` and captures
   * the per-photon SSP arrays the reference derived (monte_carlo3D.py:1575-1588, 1612),
   * every uniform the walk consumed, in consumption order, with per-photon offsets (for replay mode).
 
-Nothing here travels to the GPU box (``/root/reference`` does not exist there); ``oracle/make_golden.py`` uses it
-to write the committed fixtures under ``tests/golden/``.  Never imported by the product package.
+``oracle/make_golden.py`` uses it to write the committed fixtures under ``tests/golden/``; ``oracle/ref_timing.py``
+uses it to time the reference's Python path as the CPU baseline of ``bench.py`` (on the GPU box from the staged,
+git-ignored copy ``oracle/_ref/reference`` -- ``/root/reference`` does not exist there; GPU tests and ``smoke()`` never
+read either).  Never imported by the product package.
 """
 import configparser
 import contextlib
@@ -23,7 +25,25 @@ import types
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get('MC3D_REFERENCE_ROOT', '/root/reference')
+# /root/reference in the build container; on the GPU box (where it does not exist) the git-ignored staging copy that
+# __graft_entry__.build() made under oracle/_ref/reference (three .py files + config.ini, never committed)
+STAGED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), '_ref', 'reference')
+REFERENCE_ROOT = os.environ.get('MC3D_REFERENCE_ROOT') or \
+    ('/root/reference' if os.path.isfile('/root/reference/monte_carloMPI/monte_carlo3D.py') else STAGED_ROOT)
+
+
+def stage_reference():
+    """Copy the reference's path sources into oracle/_ref/reference (git-ignored, not gpurun-ignored) so that the CPU
+    baseline leg of bench.py can time the unmodified reference on the GPU box.  No-op when /root/reference is absent."""
+    src = '/root/reference'
+    if not os.path.isfile(os.path.join(src, 'monte_carloMPI', 'monte_carlo3D.py')):
+        return False
+    os.makedirs(os.path.join(STAGED_ROOT, 'monte_carloMPI'), exist_ok=True)
+    for rel in ('monte_carloMPI/__init__.py', 'monte_carloMPI/monte_carlo3D.py', 'monte_carloMPI/parallelize.py',
+                'monte_carloMPI/config.ini'):
+        shutil.copyfile(os.path.join(src, rel), os.path.join(STAGED_ROOT, rel))
+    shutil.copyfile(os.path.join(src, 'monte_carloMPI', 'config.ini'), os.path.join(STAGED_ROOT, 'config.ini'))
+    return True
 
 
 def reference_available():
