@@ -29,8 +29,8 @@
 #include "mc3d_device.cuh"
 
 namespace mc3d {
-cudaError_t launch_walk(const WalkParams &P, bool impurity, int events_per_vote, int block_threads, int blocks_per_sm,
-                        int grid, cudaStream_t stream, int *occupancy);
+cudaError_t launch_walk(const WalkParams &P, bool impurity, int block_threads, int blocks_per_sm, int grid,
+                        cudaStream_t stream, int *occupancy);
 cudaError_t launch_init(const WalkParams &P, bool impurity, int sm_count, cudaStream_t stream);
 cudaError_t launch_finalize(const FinalizeParams &P, int sm_count, cudaStream_t stream);
 cudaError_t launch_replay(const ReplayParams &P, cudaStream_t stream);
@@ -173,8 +173,7 @@ struct mc3d_ctx {
     int rank = 0, world = 1;
     int blocks_per_sm = 0;   // 0 = automatic: enough lanes for >= 26 photons each, at most the resident capacity
     int block_threads = 256, refill_threshold = 4;
-    int events_per_vote = 0;   // 0 = chosen from the table (see auto_events_per_vote); MC3D_EVENTS_PER_VOTE overrides
-    struct Occupancy { bool impurity; int epv, block_threads, bps_variant, n_rows, resident; };
+    struct Occupancy { bool impurity; int block_threads, bps_variant, n_rows, resident; };
     std::vector<Occupancy> occupancy;   // resident walk-kernel blocks per SM, queried once per variant
     bool input_caching = true; // skip the upload of inputs identical to the slot's previous call
     int drain_give = -1;       // -1 = automatic (16 when other calls are in flight, else off); MC3D_DRAIN_GIVE overrides
@@ -198,15 +197,16 @@ static void array_split(uint64_t n, int parts, int k, uint64_t *begin, uint64_t 
     *count = q + ((uint64_t)k < r ? 1 : 0);
 }
 
-static void threshold40(double ssa, uint32_t *hi, uint32_t *lo)
+static void threshold40(double ssa, uint32_t *t16, uint32_t *t24)
 {
-    // absorbed iff (K + 1/2) 2^-40 >= ssa  <=>  K >= ceil(ssa 2^40 - 1/2)
+    // absorbed iff (K40 + 1/2) 2^-40 >= ssa  <=>  K40 >= T40 = ceil(ssa 2^40 - 1/2); t16 = T40 >> 24 (0x10000 when
+    // T40 == 2^40: never absorbed), t24 = T40 & 0xffffff
     double t = std::ceil(std::ldexp(ssa, 40) - 0.5);
     if (!(t > 0.0)) t = 0.0;   // also catches NaN
-    if (t >= 1099511627776.0) { *hi = 0xffffffffu; *lo = 256u; return; }
+    if (t >= 1099511627776.0) t = 1099511627776.0;
     const uint64_t T = (uint64_t)t;
-    *hi = (uint32_t)(T >> 8);
-    *lo = (uint32_t)(T & 0xffu);
+    *t16 = (uint32_t)(T >> 24);
+    *t24 = (uint32_t)(T & 0xffffffu);
 }
 
 static bool build_rows(const mc3d_params *P, const mc3d_ssp_row *table, int n_rows, DevRow *out)
@@ -221,10 +221,10 @@ static bool build_rows(const mc3d_params *P, const mc3d_ssp_row *table, int n_ro
         d.d_off = (float)(1.0 - s.g + std::ldexp(s.g, -32));
         if (s.g == 0.0) { d.omr_scale = (float)std::ldexp(1.0, -32); d.omr_off = (float)std::ldexp(1.0, -33); }
         else { d.omr_scale = -(float)std::ldexp(1.0, -32); d.omr_off = 1.0f; }
-        threshold40(s.ssa_ice, &d.t_hi, &d.t_lo);
-        threshold40(s.ssa_imp, &d.ti_hi, &d.ti_lo);
-        d.t_hot = std::min(d.t_hi, RENORM_WORD);
-        d.ti_hot = std::min(d.ti_hi, RENORM_WORD);
+        threshold40(s.ssa_ice, &d.t16, &d.t24);
+        threshold40(s.ssa_imp, &d.ti16, &d.ti24);
+        d.t_hot = std::min(d.t16, RENORM_KEY) << 16;
+        d.ti_hot = std::min(d.ti16, RENORM_KEY) << 16;
         d.pad = 0u;
         // impurity iff (w + 1/2) 2^-32 <= P_ext_imp  <=>  w <= floor(P 2^32 - 1/2)
         const double sl = std::floor(std::ldexp(s.p_ext_imp, 32) - 0.5);
@@ -239,19 +239,6 @@ static bool build_rows(const mc3d_params *P, const mc3d_ssp_row *table, int n_ro
         d.inv_ext = (float)(0.6931471805599453 / (s.ext_cff_mss * P->rho_snw));
     }
     return impurity;
-}
-
-// How many events a lane runs between two warp votes (walk_kernel's EPV): a performance-only choice.  Walks in
-// strongly absorbing or optically thin media last a few events, and a stopped lane should be noticed at once;
-// long walks amortise the vote over 4 events.  Judged from the co-albedo of the row at the band centre.
-static int auto_events_per_vote(const mc3d_params *P, const mc3d_ssp_row *table, int n_rows)
-{
-    int c = (int)std::lrint(P->wvl0_um * 100.0) - P->k_first;
-    c = std::max(0, std::min(n_rows - 1, c));
-    const double coalb = 1.0 - table[c].ssa_ice;
-    if (coalb >= 0.2 || P->tau_tot < 1.0 || (P->flags & MC3D_FLAG_LAMBERT_SURFACE)) return 1;
-    if (coalb >= 0.02 || P->tau_tot < 8.0) return 2;
-    return 4;
 }
 
 // np.linspace(start, stop, n + 1): arange * step + start with the endpoint forced (numpy/_core/function_base.py)
@@ -274,10 +261,10 @@ static size_t records_layout(uint64_t n, size_t off[6])
     return at;
 }
 
-static void philox_round_keys(uint64_t seed, uint32_t rk[20])
+static void philox_round_keys(uint64_t seed, uint32_t rk[2 * PHILOX_ROUNDS])
 {
     uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < PHILOX_ROUNDS; ++r) {
         rk[2 * r] = k0;
         rk[2 * r + 1] = k1;
         k0 += PHILOX_W0;
@@ -338,9 +325,7 @@ static int init_device(Device &d, int id)
 
 static void apply_env(mc3d_ctx *ctx)
 {
-    const char *e = getenv("MC3D_EVENTS_PER_VOTE");   // experiments only; results do not depend on it
-    if (e && *e) ctx->events_per_vote = atoi(e);
-    e = getenv("MC3D_DRAIN_GIVE");                    // experiments only; results do not depend on it
+    const char *e = getenv("MC3D_DRAIN_GIVE");        // experiments only; results do not depend on it
     if (e && *e) ctx->drain_give = std::max(0, std::min(31, atoi(e)));
 }
 
@@ -554,7 +539,7 @@ static int run_async_impl(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, con
     memset(&W, 0, sizeof W);
     philox_round_keys(seed, W.rk);
     W.mu0x = (float)std::sin(P->theta0_rad);
-    if (W.mu0x == 0.0f) W.mu0x = -1e-15f;   // vertical incidence: see scatter_and_move (reproduces the muz_0 == -1 branch)
+    if (W.mu0x == 0.0f) W.mu0x = -1e-12f;   // vertical incidence: see scatter_and_move (reproduces the muz_0 == -1 branch)
     W.mu0z = (float)(-std::cos(P->theta0_rad));
     W.tau_tot = (float)(P->tau_tot / 0.6931471805599453);   // the walk's depth unit is ln 2 optical depths
     W.neg_tau_tot = -W.tau_tot;
@@ -568,7 +553,7 @@ static int run_async_impl(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, con
     }
     W.lambert_bottom = (P->flags & MC3D_FLAG_LAMBERT_BOTTOM) ? 1u : 0u;
     W.lambert_surface = (P->flags & MC3D_FLAG_LAMBERT_SURFACE) ? 1u : 0u;
-    threshold40(P->r_lambert, &W.surf_t_hi, &W.surf_t_lo);
+    threshold40(P->r_lambert, &W.surf_t16, &W.surf_t24);
     W.refill_threshold = (uint32_t)ctx->refill_threshold;
     {   // drain-phase consolidation pays when other launches can use the issue slots it frees, i.e. when other
         // calls are in flight on this context; a call running alone would only see its tail get longer
@@ -686,15 +671,14 @@ static int run_async_impl(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, con
         // as keep >= 26 photons per lane (at most the resident capacity, at least one block per SM).  Small
         // launches then leave room for the next calls in flight on the other slots' streams.
         const int bps_variant = ctx->blocks_per_sm > 0 ? ctx->blocks_per_sm : 1024 / ctx->block_threads;
-        const int epv = ctx->events_per_vote > 0 ? ctx->events_per_vote : auto_events_per_vote(P, table, n_rows);
         int resident = 0;
         for (const mc3d_ctx::Occupancy &o : ctx->occupancy)
-            if (o.impurity == impurity && o.epv == epv && o.block_threads == ctx->block_threads && o.bps_variant == bps_variant && o.n_rows == n_rows)
+            if (o.impurity == impurity && o.block_threads == ctx->block_threads && o.bps_variant == bps_variant && o.n_rows == n_rows)
                 resident = o.resident;
         if (resident == 0) {
             WalkParams Wq = W;
-            CUDA_TRY(launch_walk(Wq, impurity, epv, ctx->block_threads, bps_variant, 0, s.stream, &resident));
-            if (resident > 0) ctx->occupancy.push_back({impurity, epv, ctx->block_threads, bps_variant, n_rows, resident});
+            CUDA_TRY(launch_walk(Wq, impurity, ctx->block_threads, bps_variant, 0, s.stream, &resident));
+            if (resident > 0) ctx->occupancy.push_back({impurity, ctx->block_threads, bps_variant, n_rows, resident});
         }
         if (resident < 1) return fail(MC3D_ECUDA, "walk kernel does not fit on an SM (block %d, rows %d)", ctx->block_threads, n_rows);
         resident = std::min(resident, bps_variant);
@@ -720,7 +704,7 @@ static int run_async_impl(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, con
             const int grid = std::max(1, std::min(st.grid_blocks, want));
             CUDA_TRY(cudaEventRecord(s.ev[2 * c], s.stream));
             CUDA_TRY(launch_init(Wc, impurity, d.sm_count, s.stream));
-            CUDA_TRY(launch_walk(Wc, impurity, epv, ctx->block_threads, bps_variant, grid, s.stream, nullptr));
+            CUDA_TRY(launch_walk(Wc, impurity, ctx->block_threads, bps_variant, grid, s.stream, nullptr));
             FinalizeParams F;
             memset(&F, 0, sizeof F);
             F.raw = s.raw.p;

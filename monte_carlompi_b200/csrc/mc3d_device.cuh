@@ -1,15 +1,33 @@
 // mc3d_device.cuh -- types shared by the walk / finalize / replay kernels and the host runtime.
 //
 // Random-number layout (identical in oracle/mc3d_oracle.c, which is how production mode is checked):
-//   Philox4x32-10, key = (seed_lo, seed_hi), counter = (c0, c1, pid_lo, pid_hi), pid = global photon id.
-//   c1 low byte is the stream tag:
-//     TAG_EVENT      c0 = event number i (1-based).  w0 -> r1 of Henyey_Greenstein2 (reference
-//                    monte_carlo3D.py:915-916), w1 -> azimuth (921), w2 -> free path (1014),
-//                    (w3<<8 | w1&0xff) -> 40-bit single-scatter-albedo variate (1020)
-//     TAG_SPECIES    c0 = i>>2, word i&3 -> ice/impurity choice (1023); drawn only when an impurity is present
-//     TAG_LAMBERT    c0 = i; sub-block 0 word 0 -> bottom reflectance draw (1422/1453); sub-block 1+(j>>1),
-//                    words 2(j&1), 2(j&1)+1 -> attempt j of the cosine-law rejection loop (1245-1246)
-//     TAG_WAVELENGTH c0 = 0; w0, w1 -> Box-Muller normal for the photon's wavelength (1519)
+//   Philox4x32-7 (Salmon et al., SC'11: seven rounds is the Crush-resistant round count of Philox4x32; Random123's
+//   philox4x32_R(7, ...)), key = (seed_lo, seed_hi), counter = (c0, c1, pid_lo, pid_hi), pid = global photon id.
+//   c1 low byte is the stream tag, c1 >> 8 a sub-block:
+//     TAG_WALK       c0 = block number 3 G + b of the photon's walk stream.  The walk stream is consumed in GROUPS of
+//                    four events = three blocks = twelve words; slot s of group G uses words 3s, 3s+1, 3s+2:
+//                      word 3s   -> r1 of Henyey_Greenstein2 (reference monte_carlo3D.py:915-916)
+//                      word 3s+1 -> azimuth (921)
+//                      word 3s+2 -> free path (1014)
+//                    (the float conversions of these words ignore their low byte) and the event's 40-bit
+//                    single-scatter-albedo variate (1020) is K40 = key16 << 24 | fine24 with
+//                      key16  = (low byte of word 3s) << 8 | low byte of word 3s+2
+//                      fine24 = top 24 bits of word 0 of block (c0 = event number i, TAG_FINE) -- only ever needed
+//                               when key16 equals the top 16 bits of the threshold (probability 2^-16 per event).
+//                    An event "needs attention" when the photon left the slab or key16 >= min(T40 >> 24, 0xffc0)
+//                    (possible absorption; above 0xffc0 the direction is renormalised).  A photon that survives an
+//                    event needing attention continues with slot 0 of the NEXT group: the rest of the current
+//                    group is skipped.  This is a property of the photon's own history, so the stream -- and every
+//                    result -- is independent of how lanes, warps and GPUs are scheduled.
+//     TAG_SPECIES    c0 = i >> 2, word i & 3 -> ice/impurity choice of event i (1023); drawn only when an impurity is present
+//     TAG_LAMBERT    c0 = i.  Sub-block 0: word 0 -> bottom reflectance draw of event i (1422/1453); words 1, 2, 3 ->
+//                    azimuth, free path and absorption variate (K40 = w3 << 8 | w1 & 0xff) of event i when it IS a
+//                    Lambertian reflection (the event after a reflecting bottom hit, or any event >= 2 in
+//                    Lambertian_surface mode).  Sub-block 1+(j>>1), words 2(j&1), 2(j&1)+1 -> attempt j of the
+//                    cosine-law rejection loop (1245-1246)
+//     TAG_FIRST      c0 = 0: w0, w1 -> Box-Muller normal for the photon's wavelength (1519); w2 -> free path of event 1,
+//                    (w3 << 8 | w2 & 0xff) -> absorption variate of event 1 (initial_pdfs, 1035-1038)
+//     TAG_FINE       c0 = i: see TAG_WALK
 //   A 32-bit word w maps to the open-interval uniform (w + 0.5) 2^-32.
 #pragma once
 #include <cstdint>
@@ -17,7 +35,9 @@
 
 namespace mc3d {
 
-constexpr uint32_t TAG_EVENT = 0, TAG_SPECIES = 1, TAG_LAMBERT = 2, TAG_WAVELENGTH = 3;
+constexpr uint32_t TAG_WALK = 0, TAG_SPECIES = 1, TAG_LAMBERT = 2, TAG_FIRST = 3, TAG_FINE = 4;
+constexpr int PHILOX_ROUNDS = 7;
+constexpr uint32_t GROUP_EVENTS = 4, GROUP_BLOCKS = 3;
 constexpr uint32_t PHILOX_M0 = 0xD2511F53u, PHILOX_M1 = 0xCD9E8D57u;
 constexpr uint32_t PHILOX_W0 = 0x9E3779B9u, PHILOX_W1 = 0xBB67AE85u;
 constexpr int N_COND = 8;
@@ -29,23 +49,24 @@ struct DevRow {
     float one_m_g2;   // 1 - g^2
     float d_scale;    // 2 g 2^-32:      D = 1 - g + 2 g r = fma(float(w), d_scale, d_off), r = (w + 1/2) 2^-32
     float d_off;      // 1 - g + g 2^-32
-    uint32_t t_hot;   // coarse "needs attention" threshold on the absorption word: min(t_hi, RENORM_WORD).  It fires
-                      // on every possible absorption and, with probability >= 2^-10 per event, just to renormalise
+    uint32_t t_hot;   // coarse "needs attention" threshold on the event's key word (key16 in its top half):
+                      // min(t16, RENORM_KEY) << 16.  It fires on every possible absorption and, with probability
+                      // 2^-10 per event, just to renormalise
     float omr_scale;  // 1 - r = fma(float(w), omr_scale, omr_off): (-2^-32, 1).  For g == 0 rows (+2^-32, 2^-33),
     float omr_off;    //   i.e. r itself, which maps the factored HG form onto the reference's `1 - 2r` branch
     uint32_t ti_hot;  // t_hot of the impurity species
-    // -- resolve / finalize only
-    uint32_t t_hi;    // ice: absorbed iff K40 >= T40 = ceil(ssa 2^40 - 1/2); t_hi = T40 >> 8 (saturated)
-    uint32_t t_lo;    //      t_lo = T40 & 0xff, or 256 when T40 == 2^40 (never absorbed)
-    uint32_t ti_hi;   // same for the impurity's single-scatter albedo
-    uint32_t ti_lo;
+    // -- resolve / prologue only
+    uint32_t t16;     // ice: absorbed iff K40 >= T40 = ceil(ssa 2^40 - 1/2); t16 = T40 >> 24 (0x10000: never absorbed)
+    uint32_t t24;     //      t24 = T40 & 0xffffff
+    uint32_t ti16;    // same for the impurity's single-scatter albedo
+    uint32_t ti24;
     uint32_t s_last;  // impurity iff species word <= s_last (and s_any)
     uint32_t s_any;   // 0 when P_ext_imp == 0 (species word never selects the impurity)
     float inv_ext;    // ln 2 / (ext_cff_mss rho_snw): metres per unit of the walk's depth scale (optical depth / ln 2)
     uint32_t pad;
 };
 static_assert(sizeof(DevRow) == 64, "DevRow is 64 bytes");
-constexpr uint32_t RENORM_WORD = 0xffc00000u;   // an absorption word at/above this also triggers renormalisation (2^-10)
+constexpr uint32_t RENORM_KEY = 0xffc0u;   // a key16 at/above this also triggers renormalisation (2^-10 per event)
 
 // Raw result of one walk (32 B, one sector, written by the lane that finished the photon).
 struct __align__(16) RawResult {
@@ -65,7 +86,7 @@ struct __align__(16) Fresh {
 };
 
 struct WalkParams {
-    uint32_t rk[20];        // Philox round keys: rk[2r], rk[2r+1] for round r
+    uint32_t rk[2 * PHILOX_ROUNDS];   // Philox round keys: rk[2r], rk[2r+1] for round r
     float mu0x, mu0z;       // sin(theta0), -cos(theta0)
     float neg_tau_tot;      // -tau_tot / ln 2: depths and paths are carried in units of ln 2 optical depths, so that
     float tau_tot;          //  tau_tot / ln 2   a free path is just -log2(u) (no multiply by ln 2 per event)
@@ -76,7 +97,7 @@ struct WalkParams {
     uint32_t lambert_bottom;
     uint32_t refill_threshold;
     uint32_t lambert_surface;   // run(Lambertian_surface=True): the init kernel finishes every photon by itself
-    uint32_t surf_t_hi, surf_t_lo;   // 40-bit threshold of the surface reflectance (ssa_event = R, monte_carlo3D.py:1385-1387)
+    uint32_t surf_t16, surf_t24;   // 40-bit threshold of the surface reflectance (ssa_event = R, monte_carlo3D.py:1385-1387)
     uint32_t drain_give;    // drain phase: a warp with <= this many photons hands them to the block's pool (0 = off)
     uint64_t photon_begin;  // global id of photon 0 of this launch
     uint32_t n_photon;      // photons in this launch (< 2^31)
@@ -140,44 +161,51 @@ __device__ __forceinline__ void philox_round(uint32_t &c0, uint32_t &c1, uint32_
     c3 = l0;
 }
 
-// rk: 20 precomputed round keys (kernel parameter space -> constant bank operands of the LOP3s)
-__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                               const uint32_t *__restrict__ rk)
+// rk: precomputed round keys rk[2r], rk[2r+1] (kernel parameter space -> constant bank operands of the LOP3s)
+__device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                            const uint32_t *__restrict__ rk)
 {
 #pragma unroll
-    for (int r = 0; r < 10; ++r) philox_round(c0, c1, c2, c3, rk[2 * r], rk[2 * r + 1]);
+    for (int r = 0; r < PHILOX_ROUNDS; ++r) philox_round(c0, c1, c2, c3, rk[2 * r], rk[2 * r + 1]);
     return make_uint4(c0, c1, c2, c3);
 }
 
-// Event block (tag TAG_EVENT = 0) with the photon-constant part of rounds 1 and 2 hoisted out of the walk:
+// Walk-stream block (tag TAG_WALK = 0) with the photon-constant part of rounds 1 and 2 hoisted out of the walk:
 //   round 1 multiplies M1 by counter word 2 = pid_lo, round 2 multiplies M0 by the round-1 word 0, which depends on
-//   pid only.  pB = lo(M1 pid_lo), (pC, pD) = mulhilo(M0, hi(M1 pid_lo) ^ TAG_EVENT ^ rk[0]) are computed once per
-//   photon (philox_event_constants); 18 instead of 20 wide multiplies per event, identical output.
-struct PhiloxEventConst { uint32_t pB, pC, pD; };
+//   pid only.  pB = lo(M1 pid_lo), (pC, pD) = mulhilo(M0, hi(M1 pid_lo) ^ TAG_WALK ^ rk[0]) are computed once per
+//   photon (philox_walk_constants); 2 R - 2 instead of 2 R wide multiplies per block, identical output.
+struct PhiloxWalkConst { uint32_t pB, pC, pD; };
 
-__device__ __forceinline__ PhiloxEventConst philox_event_constants(uint32_t plo, const uint32_t *__restrict__ rk)
+__device__ __forceinline__ PhiloxWalkConst philox_walk_constants(uint32_t plo, const uint32_t *__restrict__ rk)
 {
-    PhiloxEventConst k;
-    const uint32_t a = __umulhi(PHILOX_M1, plo) ^ TAG_EVENT ^ rk[0];
+    PhiloxWalkConst k;
+    const uint32_t a = __umulhi(PHILOX_M1, plo) ^ TAG_WALK ^ rk[0];
     k.pB = PHILOX_M1 * plo;
     k.pC = __umulhi(PHILOX_M0, a);
     k.pD = PHILOX_M0 * a;
     return k;
 }
 
-__device__ __forceinline__ uint4 philox_event(uint32_t i, uint32_t phi, const PhiloxEventConst k, const uint32_t *__restrict__ rk)
+// == philox4x32(n, TAG_WALK, plo, phi)
+__device__ __forceinline__ uint4 philox_walk(uint32_t n, uint32_t phi, const PhiloxWalkConst k, const uint32_t *__restrict__ rk)
 {
-    // round 1: (c0, c1, c2, c3) = (i, TAG_EVENT, plo, phi)
-    uint32_t c2 = __umulhi(PHILOX_M0, i) ^ phi ^ rk[1];
-    uint32_t c3 = PHILOX_M0 * i;
+    // round 1: (c0, c1, c2, c3) = (n, TAG_WALK, plo, phi)
+    uint32_t c2 = __umulhi(PHILOX_M0, n) ^ phi ^ rk[1];
+    uint32_t c3 = PHILOX_M0 * n;
     // round 2: word 0 of round 1 is photon-constant, its products are pC (hi) and pD (lo)
     uint32_t c0 = __umulhi(PHILOX_M1, c2) ^ k.pB ^ rk[2];
     uint32_t c1 = PHILOX_M1 * c2;
     c2 = k.pC ^ c3 ^ rk[3];
     c3 = k.pD;
 #pragma unroll
-    for (int r = 2; r < 10; ++r) philox_round(c0, c1, c2, c3, rk[2 * r], rk[2 * r + 1]);
+    for (int r = 2; r < PHILOX_ROUNDS; ++r) philox_round(c0, c1, c2, c3, rk[2 * r], rk[2 * r + 1]);
     return make_uint4(c0, c1, c2, c3);
+}
+
+// 40-bit absorption test K40 >= T40 with T40 = t16 << 24 | t24 (t16 = 0x10000: never)
+__device__ __forceinline__ bool absorbed40(unsigned long long k40, uint32_t t16, uint32_t t24)
+{
+    return k40 >= (((unsigned long long)t16 << 24) | t24);
 }
 
 __device__ __forceinline__ float u32_to_unit(uint32_t w)

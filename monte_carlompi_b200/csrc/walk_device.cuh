@@ -10,13 +10,14 @@ namespace mc3d {
 // Walk state of the photon a lane is carrying.
 struct Lane {
     float z, ux, uy, uz;
-    float path_lo, path_hi;   // path in optical-depth units: path_hi + path_lo (flushed every 256 events)
+    float path_lo, path_hi;   // path in optical-depth units: path_hi + path_lo (flushed at every renormalisation)
     uint32_t i;               // events completed; 0 = the lane carries no photon
+    uint32_t blk;             // next block of the photon's walk stream (3 x the number of groups started)
     uint32_t plo;             // low word of the global photon id (Philox counter word 2); the high word is the
                               // same for every photon of a launch (the host never lets a launch cross 2^32)
     uint32_t row_addr;        // shared-space address of rows[row] (the hot loop loads the row constants through it)
-    uint32_t w3;              // absorption word of the last event (for the deferred fine test)
-    PhiloxEventConst pk;      // photon-constant part of the event block's first two Philox rounds
+    uint32_t key;             // key word of the last event: key16 (coarse absorption variate) in its top half
+    PhiloxWalkConst pk;       // photon-constant part of a walk block's first two Philox rounds
     bool imp;                 // last event's extinction was by the impurity
 };
 
@@ -75,7 +76,7 @@ __device__ __forceinline__ bool species_is_impurity(const WalkParams &P, const D
                                                     uint32_t phi)
 {
     if (!R.s_any) return false;
-    const uint4 v = philox4x32_10(i >> 2, TAG_SPECIES, plo, phi, P.rk);
+    const uint4 v = philox4x32(i >> 2, TAG_SPECIES, plo, phi, P.rk);
     const uint32_t sel = i & 3u;
     const uint32_t w = sel == 0 ? v.x : sel == 1 ? v.y : sel == 2 ? v.z : v.w;
     return w <= R.s_last;
@@ -83,53 +84,57 @@ __device__ __forceinline__ bool species_is_impurity(const WalkParams &P, const D
 
 constexpr uint32_t ALIVE = 0;
 
-// The scattering part of event L.i+1 given its Philox block w: HG deflection, azimuth, rotation, move.
+// The scattering part of an event given its three words: HG deflection, azimuth, rotation, move.
 // monte_carlo3D.py:1252-1281 (deflection + rotation), 1352 (move), 1372 (path).  No termination logic.
-__device__ __forceinline__ void scatter_and_move(Lane &L, const HotRow &H, const uint4 w)
+__device__ __forceinline__ void scatter_and_move(Lane &L, const HotRow &H, uint32_t w_hg, uint32_t w_az, uint32_t w_fp)
 {
     // Henyey-Greenstein inverse CDF (790-800) in a cancellation-free form:
     //   D = 1 - g + 2 g r,  s = (1 - g^2)/D,  1 - cos = (1 - g)(1 - r)(s + 1 - g)/D,  sin^2 = (1 - cos)(1 + cos)
-    const float wf = __uint2float_rn(w.x);
+    const float wf = __uint2float_rn(w_hg);
     const float invD = rcp_fast(fmaf(wf, H.d_scale, H.d_off));          // D = 1 - g + 2 g r
     const float omr = fmaf(wf, H.omr_scale, H.omr_off);                 // 1 - r  (r itself for a g == 0 row)
     const float s = H.one_m_g2 * invD;
     const float omc = (H.one_m_g * invD) * (omr * (s + H.one_m_g));
     const float ct = 1.0f - omc;
-    const float st = sqrt_fast(omc * (2.0f - omc));
+    const float st2 = omc * (2.0f - omc);                               // sin^2
     float cp, sp;
-    azimuth(w.y, cp, sp);
+    azimuth(w_az, cp, sp);
     // rotate the direction cosines, monte_carlo3D.py:1270-1281, with sqrt(1 - muz^2) taken as sqrt(mux^2 + muy^2).
     // The reference's muz_0 == +-1 branches (1262-1269) need no code here: vertical incidence enters the walk as
     // (-1e-15, 0, -1), for which this formula reproduces the muz_0 == -1 branch exactly (the host sets mu0x), and
-    // the step after a Lambertian reflection is taken in resolve().  The clamp only keeps a (never observed)
-    // exactly vertical direction finite.
-    const float d2 = fmaxf(fmaf(L.ux, L.ux, L.uy * L.uy), 1e-30f);
-    const float a = st * rsqrt_fast(d2);
+    // the step after a Lambertian reflection is taken in resolve().  sin(theta) / d and sin(theta) d come from ONE
+    // rsqrt: with q = sin^2 d^2, sin / d = sin^2 rsqrt(q) and sin d = q rsqrt(q).  The clamp only keeps an exactly
+    // forward scattering (sin^2 == 0) or a (never observed) exactly vertical direction finite.
+    const float d2 = fmaf(L.ux, L.ux, L.uy * L.uy);
+    const float q = fmaxf(st2 * d2, 1e-36f);
+    const float rq = rsqrt_fast(q);
+    const float a = st2 * rq;
     const float uzc = L.uz * cp;
     const float nx = fmaf(a, fmaf(L.ux, uzc, -L.uy * sp), L.ux * ct);
     const float ny = fmaf(a, fmaf(L.uy, uzc, L.ux * sp), L.uy * ct);
-    const float nz = fmaf(-(d2 * a), cp, L.uz * ct);
+    const float nz = fmaf(-(q * rq), cp, L.uz * ct);
     L.ux = nx; L.uy = ny; L.uz = nz;
-    const float dtau = free_path(w.z);
+    const float dtau = free_path(w_fp);
     L.z = fmaf(dtau, nz, L.z);
     L.path_lo += dtau;
-    L.w3 = w.w;
+    // key16 = (low byte of the HG word) << 8 | low byte of the free-path word, in the top half of the key word
+    L.key = __byte_perm(w_hg, w_fp, 0x0451);
 }
 
-// "Something may have happened": the photon left the slab, or its absorption word is at/above the row's coarse
-// threshold t_hot = min(t_hi, RENORM_WORD) -- every possible absorption, plus a 2^-10 chance per event that only
-// serves to renormalise the direction and flush the path accumulator (a pseudo-random but per-photon deterministic
-// schedule, mean period <= 1024 events, with no extra instruction in the loop).  Resolved later, by resolve().
+// "Something may have happened": the photon left the slab, or its key is at/above the row's coarse threshold
+// t_hot = min(t16, RENORM_KEY) << 16 -- every possible absorption, plus a 2^-10 chance per event that only serves to
+// renormalise the direction and flush the path accumulator (a pseudo-random but per-photon deterministic schedule,
+// mean period <= 1024 events, with no extra instruction in the loop).  Resolved later, by resolve().
 __device__ __forceinline__ bool needs_attention(const WalkParams &P, const Lane &L, uint32_t thi)
 {
-    return L.z > 0.0f || L.z < P.neg_tau_tot || L.w3 >= thi;
+    return L.z > 0.0f || L.z < P.neg_tau_tot || L.key >= thi;
 }
 
 // Resolve the reference's termination chain monte_carlo3D.py:1390-1466, in its order, for the event L.i that
 // just moved the photon to L.z along L.uz.  Executed by all lanes of a warp that need it at once (deferred), so it
 // is off the hot path.  On a Lambertian-bottom reflection it also performs the NEXT event (1238-1250: cosine-law
 // rejection sampling about +z) so that the hot loop never carries a bottom_reflection flag.
-// Returns the condition (0 = keep walking; the lane's state is then ready for the next event).
+// Returns the condition (0 = keep walking; the lane's state is then ready for the next group of its walk stream).
 template <bool IMP>
 __device__ __forceinline__ uint32_t resolve(const WalkParams &P, const DevRow &R, Lane &L)
 {
@@ -143,14 +148,14 @@ __device__ __forceinline__ uint32_t resolve(const WalkParams &P, const DevRow &R
         L.z = P.neg_tau_tot;
         cond = (L.i == 1u) ? 3u : 2u;
         if (P.lambert_bottom) {
-            const uint4 b = philox4x32_10(L.i, TAG_LAMBERT, L.plo, phi, P.rk);
+            const uint4 b = philox4x32(L.i, TAG_LAMBERT, L.plo, phi, P.rk);
             if ((long long)b.x <= P.refl_thr) {
-                // ---- reflected by the Lambertian bottom: event i+1 happens here ----
+                // ---- reflected by the Lambertian bottom: event i+1 happens here, on its own TAG_LAMBERT blocks ----
                 L.i += 1u;
-                const uint4 w = philox4x32_10(L.i, TAG_EVENT, L.plo, phi, P.rk);
+                const uint4 w = philox4x32(L.i, TAG_LAMBERT, L.plo, phi, P.rk);
                 float ct, st;
                 for (uint32_t j = 0;; ++j) {
-                    const uint4 a = philox4x32_10(L.i, TAG_LAMBERT | ((1u + (j >> 1)) << 8), L.plo, phi, P.rk);
+                    const uint4 a = philox4x32(L.i, TAG_LAMBERT | ((1u + (j >> 1)) << 8), L.plo, phi, P.rk);
                     const float u_t = u32_to_unit((j & 1u) ? a.z : a.x);
                     const float r1 = u32_to_unit((j & 1u) ? a.w : a.y);
                     float s_, c_;
@@ -163,7 +168,7 @@ __device__ __forceinline__ uint32_t resolve(const WalkParams &P, const DevRow &R
                 const float dt2 = free_path(w.z);
                 L.z = fmaf(dt2, ct, P.neg_tau_tot);
                 L.path_lo += dt2;
-                L.w3 = w.w;
+                L.key = w.w;
                 L.imp = IMP ? species_is_impurity(P, R, L.i, L.plo, phi) : false;
                 cond = ALIVE;
                 if (L.z > 0.0f) {
@@ -173,16 +178,17 @@ __device__ __forceinline__ uint32_t resolve(const WalkParams &P, const DevRow &R
             }
         }
     }
-    if (cond == ALIVE) {   // 1461-1466: absorbed iff the 40-bit variate (w3 << 8 | low byte of w1) >= T40
-        const uint32_t t_hi = L.imp ? R.ti_hi : R.t_hi, t_lo = L.imp ? R.ti_lo : R.t_lo;
-        bool absorbed = L.w3 > t_hi;
-        if (L.w3 == t_hi) {   // probability 2^-32: regenerate the event's block for the low byte
-            const uint4 w = philox4x32_10(L.i, TAG_EVENT, L.plo, phi, P.rk);
-            absorbed = (w.y & 0xffu) >= t_lo;
+    const uint32_t key16 = L.key >> 16;
+    if (cond == ALIVE) {   // 1461-1466: absorbed iff K40 = key16 << 24 | fine24 >= T40
+        const uint32_t t16 = L.imp ? R.ti16 : R.t16;
+        bool absorbed = key16 > t16;
+        if (key16 == t16) {   // probability 2^-16: the low 24 bits of the variate come from the event's TAG_FINE block
+            const uint4 f = philox4x32(L.i, TAG_FINE, L.plo, phi, P.rk);
+            absorbed = (f.x >> 8) >= (L.imp ? R.ti24 : R.t24);
         }
         if (absorbed) cond = L.imp ? 5u : 4u;
     }
-    if (cond == ALIVE && L.w3 >= RENORM_WORD) {   // keyed on the photon's own random stream: scheduling independent
+    if (cond == ALIVE && key16 >= RENORM_KEY) {   // keyed on the photon's own random stream: scheduling independent
         const float rn = rsqrt_fast(fmaf(L.ux, L.ux, fmaf(L.uy, L.uy, L.uz * L.uz)));
         L.ux *= rn; L.uy *= rn; L.uz *= rn;
         L.path_hi += L.path_lo;
@@ -191,44 +197,122 @@ __device__ __forceinline__ uint32_t resolve(const WalkParams &P, const DevRow &R
     return cond;
 }
 
-// One scattering event of the photon in L (event number L.i + 1) up to and including the attention predicate.
-// Returns true while the photon simply keeps walking.
+// One scattering event of the photon in L from three words of its walk stream, up to and including the attention
+// predicate.  Returns true while the photon simply keeps walking.
 template <bool IMP>
-__device__ __forceinline__ bool event(const WalkParams &P, const DevRow *rows, uint32_t rows_addr, Lane &L)
+__device__ __forceinline__ bool event(const WalkParams &P, const DevRow *rows, uint32_t rows_addr, Lane &L, const HotRow &H,
+                                      uint32_t w_hg, uint32_t w_az, uint32_t w_fp)
 {
-    const HotRow H = load_hot_row(L.row_addr);
-    const uint32_t phi = (uint32_t)(P.photon_begin >> 32);
-    const uint4 w = philox_event(L.i + 1u, phi, L.pk, P.rk);   // == philox4x32_10(i + 1, TAG_EVENT, plo, phi)
     L.i += 1u;
-    scatter_and_move(L, H, w);
+    scatter_and_move(L, H, w_hg, w_az, w_fp);
     uint32_t thi = H.t_hot;
     if (IMP) {
         const DevRow &R = rows[lane_row(L, rows_addr)];
-        L.imp = species_is_impurity(P, R, L.i, L.plo, phi);
+        L.imp = species_is_impurity(P, R, L.i, L.plo, (uint32_t)(P.photon_begin >> 32));
         thi = L.imp ? H.ti_hot : thi;
     }
     return !needs_attention(P, L, thi);
 }
 
-// Latency-oriented form of event() for the drain phase, where a warp runs (almost) alone on its scheduler and the
-// dependent chain of one event, not the issue rate, sets the pace: `wn` holds the Philox block of event L.i + 1 on
-// entry and of the event after it on exit, so the next block's multiply chain overlaps this event's scattering math.
-template <bool IMP>
-__device__ __forceinline__ bool event_pipelined(const WalkParams &P, const DevRow *rows, uint32_t rows_addr, Lane &L, uint4 &wn)
+// One GROUP of the photon's walk stream: up to four events on three Philox blocks (twelve words, three per event).
+// The lane stops at the first event that needs attention; if the photon survives it continues with the NEXT group
+// (L.blk already points there).  EAGER computes the three blocks up front (three independent multiply chains that
+// overlap the events' arithmetic: the latency-oriented form used when a warp runs almost alone, i.e. while a launch
+// drains); otherwise each block is computed right before the event that first needs it.
+template <bool IMP, bool EAGER>
+__device__ __forceinline__ bool group(const WalkParams &P, const DevRow *rows, uint32_t rows_addr, Lane &L)
 {
     const HotRow H = load_hot_row(L.row_addr);
     const uint32_t phi = (uint32_t)(P.photon_begin >> 32);
-    const uint4 w = wn;
-    wn = philox_event(L.i + 2u, phi, L.pk, P.rk);
-    L.i += 1u;
-    scatter_and_move(L, H, w);
-    uint32_t thi = H.t_hot;
-    if (IMP) {
-        const DevRow &R = rows[lane_row(L, rows_addr)];
-        L.imp = species_is_impurity(P, R, L.i, L.plo, phi);
-        thi = L.imp ? H.ti_hot : thi;
+    const uint32_t n = L.blk;
+    L.blk = n + GROUP_BLOCKS;
+    const uint4 a = philox_walk(n, phi, L.pk, P.rk);
+    uint4 b, c;
+    if (EAGER) {
+        b = philox_walk(n + 1u, phi, L.pk, P.rk);
+        c = philox_walk(n + 2u, phi, L.pk, P.rk);
     }
-    return !needs_attention(P, L, thi);
+    if (!event<IMP>(P, rows, rows_addr, L, H, a.x, a.y, a.z)) return false;
+    if (!EAGER) b = philox_walk(n + 1u, phi, L.pk, P.rk);
+    if (!event<IMP>(P, rows, rows_addr, L, H, a.w, b.x, b.y)) return false;
+    if (!EAGER) c = philox_walk(n + 2u, phi, L.pk, P.rk);
+    if (!event<IMP>(P, rows, rows_addr, L, H, b.z, b.w, c.x)) return false;
+    return event<IMP>(P, rows, rows_addr, L, H, c.y, c.z, c.w);
+}
+
+// ---- per-photon prologue (shared by the init kernel and the fused kernel) ----------------------------------------
+
+// One photon in Lambertian_surface mode, events 2, 3, ... after an event 1 that did not absorb it.  Event 1 does
+// not move (dtau = 0, monte_carlo3D.py:1228-1229) and is absorbed with probability 1 - R (ssa_event = R,
+// 1385-1387); every later event re-emits the photon from the surface with the cosine law (1238-1250) and almost
+// surely leaves through the top on event 2.  Every event >= 2 is a Lambertian reflection event (TAG_LAMBERT blocks).
+template <bool IMP>
+__device__ __noinline__ uint32_t lambert_surface_walk(const WalkParams &P, const DevRow &R, Lane &L)
+{
+    const uint32_t phi = (uint32_t)(P.photon_begin >> 32);
+    for (;;) {
+        // termination chain for event L.i: z > 0, (z < -tau_tot cannot happen), absorbed by the surface
+        if (L.z > 0.0f) {
+            L.path_lo -= __fdividef(L.z, L.uz);
+            return 1u;
+        }
+        const uint32_t key16 = L.key >> 16;
+        bool absorbed = key16 > P.surf_t16;
+        if (key16 == P.surf_t16) absorbed = (philox4x32(L.i, TAG_FINE, L.plo, phi, P.rk).x >> 8) >= P.surf_t24;
+        if (absorbed) return L.imp ? 5u : 4u;
+        L.i += 1u;
+        const uint4 w = philox4x32(L.i, TAG_LAMBERT, L.plo, phi, P.rk);
+        float ct, st;
+        for (uint32_t j = 0;; ++j) {
+            const uint4 a = philox4x32(L.i, TAG_LAMBERT | ((1u + (j >> 1)) << 8), L.plo, phi, P.rk);
+            const float u_t = u32_to_unit((j & 1u) ? a.z : a.x);
+            const float r1 = u32_to_unit((j & 1u) ? a.w : a.y);
+            float s_, c_;
+            sincosf(1.5707963267948966f * u_t, &s_, &c_);
+            if (r1 < 2.0f * s_ * c_) { ct = c_; st = s_; break; }
+        }
+        float cp, sp;
+        azimuth(w.y, cp, sp);
+        L.ux = st * cp; L.uy = st * sp; L.uz = ct;
+        const float dt = free_path(w.z);
+        L.z = fmaf(dt, ct, L.z);
+        L.path_lo += dt;
+        L.key = w.w;
+        L.imp = IMP ? species_is_impurity(P, R, L.i, L.plo, phi) : false;
+    }
+}
+
+// Wavelength draw (monte_carlo3D.py:1515-1520: np.around(np.random.normal(wvl0, scale), 2), Box-Muller on the photon's
+// TAG_FIRST block; the rounded value is an index into the SSP table) and the first event: the three draws of
+// initial_pdfs (1035-1038), no deflection (1232-1237), move, direct-transmission / Lambertian-bottom /
+// first-extinction absorption tests (1399-1466).  On return L holds the photon's state and `row` its SSP row.
+// Returns the condition: ALIVE = the photon walks on, with L ready for group 0 of its walk stream.  L.i == 1 then
+// unless the first step hit a reflecting Lambertian bottom (event 2 has then been performed as well).
+template <bool IMP>
+__device__ __forceinline__ uint32_t first_event(const WalkParams &P, const DevRow *rows, uint32_t rows_addr, uint32_t plo,
+                                                Lane &L, uint32_t &row, float &dtau)
+{
+    const uint32_t phi = (uint32_t)(P.photon_begin >> 32);
+    const uint4 w = philox4x32(0u, TAG_FIRST, plo, phi, P.rk);
+    const float zn = sqrtf(-2.0f * logf(u32_to_unit(w.x))) * cospif(2.0f * u32_to_unit(w.y));
+    const int r = (int)rint(P.wvl0_x100 + P.sigma_x100 * (double)zn) - P.k_first;
+    row = (uint32_t)max(0, min(P.n_rows - 1, r));
+    const DevRow &R = rows[row];
+    L.plo = plo; L.row_addr = rows_addr + row * (uint32_t)sizeof(DevRow); L.blk = 0u; L.i = 1u;
+    L.ux = P.mu0x; L.uy = 0.0f; L.uz = P.mu0z; L.path_hi = 0.0f;
+    L.key = w.w;
+    L.imp = IMP ? species_is_impurity(P, R, 1u, plo, phi) : false;
+    L.pk = philox_walk_constants(plo, P.rk);
+    if (P.lambert_surface) {
+        dtau = 0.0f;
+        L.z = 0.0f; L.path_lo = 0.0f;
+        return lambert_surface_walk<IMP>(P, R, L);
+    }
+    dtau = free_path(w.z);
+    L.z = dtau * P.mu0z;
+    L.path_lo = dtau;
+    if (L.z < P.neg_tau_tot || (w.w >> 16) >= (L.imp ? R.ti16 : R.t16)) return resolve<IMP>(P, R, L);
+    return ALIVE;
 }
 
 // Finish (store the raw record, free the lane) or resume a lane whose last event needed attention.

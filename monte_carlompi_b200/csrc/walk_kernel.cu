@@ -5,10 +5,12 @@
 // body monte_carlo3D (1111-1490), plus the per-photon wavelength draw (1515-1520).
 //
 // Execution model
-//   * persistent warps; every lane walks one photon at a time.  The hot loop is one scattering event per
-//     iteration: one Philox4x32-10 block -> (HG deflection, azimuth, free path, absorption variate), rotate,
-//     move, and ONE predicate "left the top / hit the bottom / maybe absorbed / due for renormalisation".  A lane
-//     that trips it simply stops and waits.
+//   * persistent warps; every lane walks one photon at a time.  The hot loop runs one GROUP of the photon's walk
+//     stream per iteration: four scattering events on three Philox4x32-7 blocks (three words per event -> HG
+//     deflection, azimuth, free path; the coarse absorption key is made of the low bytes the float conversions
+//     ignore), each event = rotate, move, and ONE predicate "left the top / hit the bottom / maybe absorbed / due
+//     for renormalisation".  A lane that trips it simply stops and waits; if its photon survives it continues with
+//     the next group (mc3d_device.cuh: the random-number layout).
 //   * when `refill_threshold` lanes of a warp are waiting, the warp takes one uniform branch: the waiting lanes
 //     are resolved together (the reference's termination chain in its order; finished photons store one 32-byte
 //     raw record) and the empty ones pop a fresh photon from a per-warp shared-memory ring.  The ring is refilled
@@ -41,7 +43,7 @@ struct WarpRing {
 // only touched under `lock`.  `draining` counts the warps currently in phase B: a warp donates only while another
 // one is there to receive, and no warp leaves while the pool holds photons, so nothing is ever stranded.
 constexpr int POOL_CAP = 64;
-constexpr int POOL_WORDS = 9;   // z, ux, uy, uz, path_lo, path_hi, i, plo, row_addr
+constexpr int POOL_WORDS = 10;   // z, ux, uy, uz, path_lo, path_hi, i, plo, row_addr, blk
 struct DrainPool {
     uint32_t lock, count, draining, pad;
     uint32_t word[POOL_WORDS][POOL_CAP];
@@ -68,10 +70,10 @@ __device__ __forceinline__ void pool_release(DrainPool &D, uint32_t lane)
     if (lane == 0) atomicExch(&D.lock, 0u);
 }
 
-// EPV = events per lane between two warp votes (1, 2 or 4).  The vote + threshold test costs ~14 issue cycles per
-// iteration; a stopped lane idles < EPV events before it is noticed, so long walks want 4 and strongly absorbing
-// media (a few events per photon) want 1.  Results do not depend on it.
-template <bool IMP, int EPV, int BLOCK, int MIN_BLOCKS>
+// One warp vote per group of four events: the vote + threshold test costs ~14 issue cycles, and a stopped lane idles
+// at most three events before it is noticed.  (Strongly absorbing or optically thin media, a few events per photon,
+// take the fused one-thread-per-photon kernel instead: fused_kernel.cu.)
+template <bool IMP, int BLOCK, int MIN_BLOCKS>
 __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) walk_kernel(const __grid_constant__ WalkParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -92,7 +94,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) walk_kernel(const __grid_co
 
     Lane L;
     L.z = 0.f; L.ux = 0.f; L.uy = 0.f; L.uz = -1.f; L.path_lo = 0.f; L.path_hi = 0.f;
-    L.i = 0; L.plo = 0; L.row_addr = rows_addr; L.w3 = 0; L.imp = false;
+    L.i = 0; L.blk = 0; L.plo = 0; L.row_addr = rows_addr; L.key = 0; L.imp = false;
     L.pk.pB = L.pk.pC = L.pk.pD = 0;
     bool alive = false;   // false: the lane is waiting (its last event needs attention, or it carries no photon)
 
@@ -123,8 +125,9 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) walk_kernel(const __grid_co
                     const uint4 f = Q.entry[(ring_head + rank) & (RING - 1)];
                     const float dtau = __uint_as_float(f.z);
                     L.plo = (uint32_t)P.photon_begin + f.x;
-                    L.pk = philox_event_constants(L.plo, P.rk);
+                    L.pk = philox_walk_constants(L.plo, P.rk);
                     L.row_addr = rows_addr + f.y * (uint32_t)sizeof(DevRow);
+                    L.blk = 0u;
                     L.ux = P.mu0x; L.uy = 0.0f; L.uz = P.mu0z;
                     L.z = dtau * P.mu0z;
                     L.path_lo = dtau;
@@ -137,26 +140,19 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) walk_kernel(const __grid_co
             __syncwarp();
             if (exhausted) break;   // the ring is empty and the list has been handed out: drain
         }
-#pragma unroll
-        for (int u = 0; u < EPV; ++u)
-            if (alive) alive = event<IMP>(P, rows, rows_addr, L);
+        if (alive) alive = group<IMP, false>(P, rows, rows_addr, L);
     }
 
     // ---- phase B: drain.  Nothing left to hand out; every lane finishes the photon it carries.  The SM empties
-    // out, so this loop is latency-bound: it uses the software-pipelined event (next Philox block computed during
-    // the current event's math).  Warps consolidate through the block's pool (see DrainPool).
-    const uint32_t phi = (uint32_t)(P.photon_begin >> 32);
-    uint4 wn = philox_event(L.i + 1u, phi, L.pk, P.rk);
+    // out, so this loop is latency-bound: it uses the eager group (the three Philox blocks of a group are independent
+    // multiply chains that overlap the events' arithmetic).  Warps consolidate through the block's pool (see DrainPool).
     if (lane == 0) atomicAdd(&D.draining, 1u);
     const uint32_t give_max = P.drain_give;   // 0: plain drain loop (the launch runs alone)
     // Unlocked peek at the pool: (count << 8) | draining, lane 0's view, so every branch on it is warp-uniform.
     // Refreshed once per iteration, one event stale; every decision is re-made under the lock.
     uint32_t peek = 0u;
     for (;;) {
-        if (!alive && L.i != 0u) {
-            alive = resolve_lane<IMP>(P, rows, rows_addr, L);
-            if (alive) wn = philox_event(L.i + 1u, phi, L.pk, P.rk);   // a Lambertian reflection advanced the event count
-        }
+        if (!alive && L.i != 0u) alive = resolve_lane<IMP>(P, rows, rows_addr, L);
         const uint32_t alive_mask = __ballot_sync(0xffffffffu, alive);
         const uint32_t n_alive = __popc(alive_mask);
         if (give_max == 0u) {
@@ -178,6 +174,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) walk_kernel(const __grid_co
                         L.path_lo = __uint_as_float(pool_get(&D.word[4][e]));
                         L.path_hi = __uint_as_float(pool_get(&D.word[5][e]));
                         L.i = pool_get(&D.word[6][e]); L.plo = pool_get(&D.word[7][e]); L.row_addr = pool_get(&D.word[8][e]);
+                        L.blk = pool_get(&D.word[9][e]);
                         taken = true;
                     }
                     __syncwarp();
@@ -194,6 +191,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) walk_kernel(const __grid_co
                         pool_put(&D.word[4][e], __float_as_uint(L.path_lo));
                         pool_put(&D.word[5][e], __float_as_uint(L.path_hi));
                         pool_put(&D.word[6][e], L.i); pool_put(&D.word[7][e], L.plo); pool_put(&D.word[8][e], L.row_addr);
+                        pool_put(&D.word[9][e], L.blk);
                     }
                     if (lane == 0) { pool_put(&D.count, c + n_alive); atomicSub(&D.draining, 1u); }
                     leave = true;
@@ -201,15 +199,14 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) walk_kernel(const __grid_co
                 pool_release(D, lane);
                 if (leave) break;
                 if (taken) {   // outside the lock: rebuild the Philox state of the photon just taken over
-                    L.pk = philox_event_constants(L.plo, P.rk);
-                    wn = philox_event(L.i + 1u, phi, L.pk, P.rk);
+                    L.pk = philox_walk_constants(L.plo, P.rk);
                     alive = true;
                 }
             }
         }
         if (give_max != 0u)
             peek = __shfl_sync(0xffffffffu, lane == 0 ? (pool_get(&D.count) << 8) | min(pool_get(&D.draining), 255u) : 0u, 0);
-        if (alive) alive = event_pipelined<IMP>(P, rows, rows_addr, L, wn);
+        if (alive) alive = group<IMP, true>(P, rows, rows_addr, L);
     }
 }
 
@@ -220,11 +217,11 @@ size_t walk_smem_bytes(int n_rows, int block_threads)
     return ((n_rows * sizeof(DevRow) + 15) & ~size_t(15)) + (block_threads / 32) * sizeof(WarpRing) + sizeof(DrainPool);
 }
 
-template <bool IMP, int EPV, int BLOCK, int MIN_BLOCKS>
+template <bool IMP, int BLOCK, int MIN_BLOCKS>
 static cudaError_t launch_one(const WalkParams &P, int grid, cudaStream_t stream, int *occupancy)
 {
     const size_t smem = walk_smem_bytes(P.n_rows, BLOCK);
-    auto kern = walk_kernel<IMP, EPV, BLOCK, MIN_BLOCKS>;
+    auto kern = walk_kernel<IMP, BLOCK, MIN_BLOCKS>;
     if (smem > 48 * 1024) {   // only large SSP tables need the opt-in (the default table + rings + pool is ~14 KB)
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -235,35 +232,29 @@ static cudaError_t launch_one(const WalkParams &P, int grid, cudaStream_t stream
 }
 
 template <int BLOCK, int MIN_BLOCKS>
-static cudaError_t launch_variant(const WalkParams &P, bool impurity, int epv, int grid, cudaStream_t stream, int *occupancy)
+static cudaError_t launch_variant(const WalkParams &P, bool impurity, int grid, cudaStream_t stream, int *occupancy)
 {
-    if (impurity) {
-        if (epv >= 4) return launch_one<true, 4, BLOCK, MIN_BLOCKS>(P, grid, stream, occupancy);
-        if (epv >= 2) return launch_one<true, 2, BLOCK, MIN_BLOCKS>(P, grid, stream, occupancy);
-        return launch_one<true, 1, BLOCK, MIN_BLOCKS>(P, grid, stream, occupancy);
-    }
-    if (epv >= 4) return launch_one<false, 4, BLOCK, MIN_BLOCKS>(P, grid, stream, occupancy);
-    if (epv >= 2) return launch_one<false, 2, BLOCK, MIN_BLOCKS>(P, grid, stream, occupancy);
-    return launch_one<false, 1, BLOCK, MIN_BLOCKS>(P, grid, stream, occupancy);
+    if (impurity) return launch_one<true, BLOCK, MIN_BLOCKS>(P, grid, stream, occupancy);
+    return launch_one<false, BLOCK, MIN_BLOCKS>(P, grid, stream, occupancy);
 }
 
-// block_threads in {128, 256, 512}; blocks_per_sm is the occupancy target the variant is compiled for (56 / 48
+// block_threads in {128, 256, 512}; blocks_per_sm is the occupancy target the variant is compiled for (64 / 48
 // registers per thread for <= 32 / 40 resident warps per SM; 32 warps is the default: the loop is bound by the
-// issue port -- Philox's half-rate integer instructions -- and more resident warps do not raise its rate).
+// issue port and more resident warps do not raise its rate).
 // With `occupancy` non-null nothing is launched; the resident blocks per SM are returned through it.
-cudaError_t launch_walk(const WalkParams &P, bool impurity, int events_per_vote, int block_threads, int blocks_per_sm,
-                        int grid, cudaStream_t stream, int *occupancy)
+cudaError_t launch_walk(const WalkParams &P, bool impurity, int block_threads, int blocks_per_sm, int grid,
+                        cudaStream_t stream, int *occupancy)
 {
     const int warps_per_sm = block_threads / 32 * blocks_per_sm;
     if (block_threads == 128) {
-        if (warps_per_sm <= 32) return launch_variant<128, 8>(P, impurity, events_per_vote, grid, stream, occupancy);
-        return launch_variant<128, 10>(P, impurity, events_per_vote, grid, stream, occupancy);
+        if (warps_per_sm <= 32) return launch_variant<128, 8>(P, impurity, grid, stream, occupancy);
+        return launch_variant<128, 10>(P, impurity, grid, stream, occupancy);
     }
     if (block_threads == 256) {
-        if (warps_per_sm <= 32) return launch_variant<256, 4>(P, impurity, events_per_vote, grid, stream, occupancy);
-        return launch_variant<256, 5>(P, impurity, events_per_vote, grid, stream, occupancy);
+        if (warps_per_sm <= 32) return launch_variant<256, 4>(P, impurity, grid, stream, occupancy);
+        return launch_variant<256, 5>(P, impurity, grid, stream, occupancy);
     }
-    if (block_threads == 512) return launch_variant<512, 2>(P, impurity, events_per_vote, grid, stream, occupancy);
+    if (block_threads == 512) return launch_variant<512, 2>(P, impurity, grid, stream, occupancy);
     return cudaErrorInvalidValue;
 }
 

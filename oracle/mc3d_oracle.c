@@ -41,6 +41,10 @@ typedef struct {
 
 /* ---- source of uniforms: either the reference's recorded stream or Philox -------------------------------- */
 
+/* event kinds: which part of the photon's random stream an event draws from (production mode; see the layout in
+ * monte_carlompi_b200/csrc/mc3d_device.cuh and DESIGN.md "random-number layout") */
+enum { EV_FIRST = 0, EV_WALK = 1, EV_REFLECT = 2 };
+
 typedef struct {
     /* replay */
     const double *init3;   /* 3 first-step uniforms of this photon */
@@ -52,14 +56,22 @@ typedef struct {
     uint32_t key[2];
     uint64_t pid;
     int impurity_on;
+    uint32_t blk;          /* next block of the walk stream (3 x groups started) */
+    int slot;              /* next event slot of the current group; 4 = start a new group */
+    uint32_t grp[12];      /* the twelve words of the current group */
+    uint32_t first[4];     /* the TAG_FIRST block (wavelength + first event) */
+    uint32_t key16;        /* coarse absorption variate of the last event drawn */
+    uint32_t t16[2], t24[2];   /* absorption thresholds T40 = t16 << 24 | t24 of (ice, impurity / surface) */
 } draw_src;
 
-static void philox4x32_10(const uint32_t ctr_in[4], const uint32_t key_in[2], uint32_t out[4])
+#define PHILOX_ROUNDS 7
+
+static void philox4x32(int rounds, const uint32_t ctr_in[4], const uint32_t key_in[2], uint32_t out[4])
 {
-    /* Salmon, Moraes, Dror, Shaw: "Parallel random numbers: as easy as 1, 2, 3" (SC'11), Philox-4x32, 10 rounds */
+    /* Salmon, Moraes, Dror, Shaw: "Parallel random numbers: as easy as 1, 2, 3" (SC'11), Philox-4x32, R rounds */
     uint32_t c0 = ctr_in[0], c1 = ctr_in[1], c2 = ctr_in[2], c3 = ctr_in[3];
     uint32_t k0 = key_in[0], k1 = key_in[1];
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < rounds; ++r) {
         uint64_t p0 = (uint64_t)0xD2511F53u * c0;
         uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
         uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
@@ -73,16 +85,28 @@ static void philox4x32_10(const uint32_t ctr_in[4], const uint32_t key_in[2], ui
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-/* stream tags (counter word 1, low byte); see DESIGN.md "random-number layout" */
-enum { TAG_EVENT = 0, TAG_SPECIES = 1, TAG_LAMBERT = 2, TAG_WAVELENGTH = 3 };
+/* stream tags (counter word 1, low byte) */
+enum { TAG_WALK = 0, TAG_SPECIES = 1, TAG_LAMBERT = 2, TAG_FIRST = 3, TAG_FINE = 4 };
+#define RENORM_KEY 0xffc0u
 
 static void philox_block(const draw_src *s, uint32_t c0, uint32_t c1, uint32_t w[4])
 {
     uint32_t ctr[4] = {c0, c1, (uint32_t)s->pid, (uint32_t)(s->pid >> 32)};
-    philox4x32_10(ctr, s->key, w);
+    philox4x32(PHILOX_ROUNDS, ctr, s->key, w);
 }
 
 static inline double u32_to_unit(uint32_t w) { return ((double)w + 0.5) * (1.0 / 4294967296.0); }
+
+/* T40 = ceil(ssa 2^40 - 1/2) clamped to [0, 2^40]: (K40 + 1/2) 2^-40 >= ssa  <=>  K40 >= T40 */
+static void threshold40(double ssa, uint32_t *t16, uint32_t *t24)
+{
+    double t = ceil(ldexp(ssa, 40) - 0.5);
+    if (!(t > 0.0)) t = 0.0;
+    if (t >= 1099511627776.0) t = 1099511627776.0;
+    uint64_t T = (uint64_t)t;
+    *t16 = (uint32_t)(T >> 24);
+    *t24 = (uint32_t)(T & 0xffffffu);
+}
 
 static double replay_next(draw_src *s)
 {
@@ -92,8 +116,10 @@ static double replay_next(draw_src *s)
 
 typedef struct { double r1, u_phi, u_tau, u_ssa, u_ext; } event_draws;
 
-/* the 5 (3 on the first step) uniforms of event i, in the reference's order MC3D:915-921, 1014-1023, 1036-1038 */
-static void draw_event(draw_src *s, int64_t i, event_draws *d)
+/* the 5 (3 on the first step) uniforms of event i, in the reference's order MC3D:915-921, 1014-1023, 1036-1038.
+ * `species` selects whose albedo the 40-bit variate will be compared with (0 ice, 1 impurity / Lambertian surface):
+ * its low 24 bits are only drawn when the top 16 do not decide the comparison. */
+static void draw_event(draw_src *s, int64_t i, int kind, event_draws *d)
 {
     if (!s->use_philox) {
         if (i == 1) {
@@ -105,13 +131,30 @@ static void draw_event(draw_src *s, int64_t i, event_draws *d)
         }
         return;
     }
-    uint32_t w[4];
-    philox_block(s, (uint32_t)i, TAG_EVENT, w);
-    d->r1 = u32_to_unit(w[0]);
-    d->u_phi = u32_to_unit(w[1]);
-    d->u_tau = u32_to_unit(w[2]);
-    uint64_t k40 = ((uint64_t)w[3] << 8) | (w[1] & 0xFFu);
-    d->u_ssa = ((double)k40 + 0.5) * (1.0 / 1099511627776.0);
+    if (kind == EV_FIRST) {                       /* TAG_FIRST: w2 free path, top half of w3 = key16 */
+        d->r1 = d->u_phi = 0.0;
+        d->u_tau = u32_to_unit(s->first[2]);
+        s->key16 = s->first[3] >> 16;
+    } else if (kind == EV_REFLECT) {              /* TAG_LAMBERT sub-block 0 of event i: w1 azimuth, w2 free path, w3 key */
+        uint32_t w[4];
+        philox_block(s, (uint32_t)i, TAG_LAMBERT, w);
+        d->r1 = 0.0;                              /* the HG deflection is not used by a Lambertian reflection */
+        d->u_phi = u32_to_unit(w[1]);
+        d->u_tau = u32_to_unit(w[2]);
+        s->key16 = w[3] >> 16;
+    } else {                                      /* the walk stream: groups of 4 events on 3 blocks */
+        if (s->slot >= 4) {
+            for (int b = 0; b < 3; ++b) philox_block(s, s->blk + b, TAG_WALK, s->grp + 4 * b);
+            s->blk += 3;
+            s->slot = 0;
+        }
+        const uint32_t *w = s->grp + 3 * s->slot;
+        s->slot += 1;
+        d->r1 = u32_to_unit(w[0]);
+        d->u_phi = u32_to_unit(w[1]);
+        d->u_tau = u32_to_unit(w[2]);
+        s->key16 = ((w[0] & 0xFFu) << 8) | (w[2] & 0xFFu);
+    }
     if (s->impurity_on) {
         uint32_t v[4];
         philox_block(s, (uint32_t)(i >> 2), TAG_SPECIES, v);
@@ -119,6 +162,19 @@ static void draw_event(draw_src *s, int64_t i, event_draws *d)
     } else {
         d->u_ext = 1.0; /* P_ext_imp == 0: "u > 0" always holds, MC3D:1375-1379 */
     }
+    d->u_ssa = -1.0;    /* completed by draw_albedo() once the species is known */
+}
+
+/* the single-scatter-albedo uniform of event i, (K40 + 1/2) 2^-40 with K40 = key16 << 24 | fine24 */
+static double draw_albedo(draw_src *s, int64_t i, int species)
+{
+    uint64_t k40 = (uint64_t)s->key16 << 24;
+    if (s->key16 == s->t16[species]) {
+        uint32_t f[4];
+        philox_block(s, (uint32_t)i, TAG_FINE, f);
+        k40 |= f[0] >> 8;
+    }
+    return ((double)k40 + 0.5) * (1.0 / 1099511627776.0);
 }
 
 static double draw_reflectance(draw_src *s, int64_t i)
@@ -170,7 +226,8 @@ static void walk(const oracle_params *P, draw_src *src, double wvl, double ssa_i
     while (condition == 0) {
         i += 1;
         event_draws d;
-        draw_event(src, i, &d);
+        const int kind = (i == 1) ? EV_FIRST : ((lambert_surface || bottom_reflection) ? EV_REFLECT : EV_WALK);
+        draw_event(src, i, kind, &d);
         if (src->exhausted) break;
         double dtau = -log(d.u_tau);                 /* MC3D:1014, 1036, 1227 */
         if (lambert_surface && i == 1) dtau = 0;     /* MC3D:1228-1229 */
@@ -229,11 +286,18 @@ static void walk(const oracle_params *P, draw_src *src, double wvl, double ssa_i
         if (d.u_ext > p_ext_imp) { ext_state = 1; ssa_event = ssa_ice; } /* MC3D:1375-1383 */
         else { ext_state = 2; ssa_event = ssa_imp; }
         if (lambert_surface) ssa_event = P->r_lambert; /* MC3D:1385-1387 */
+        int species = (ext_state == 2) ? 1 : 0;
+        if (src->use_philox) {
+            if (lambert_surface) { species = 1; threshold40(P->r_lambert, &src->t16[1], &src->t24[1]); }
+            d.u_ssa = draw_albedo(src, i, species);
+        }
+        int attention = 0;  /* production stream layout: the event "needs attention" */
 
         if (z > 0) {                                 /* MC3D:1390-1397 */
             condition = 1;
             path_length += -((z * dtau) / ((z - z_prev) * ext_cff));
         } else if (z < -P->tau_tot) {                /* MC3D:1399-1459 (both branches share the arithmetic) */
+            attention = 1;
             path_length += -(((z + P->tau_tot) * dtau) / ((z - z_prev) * ext_cff));
             double dtau_correction = -(((z + P->tau_tot) / (z_prev - z)) * dtau);
             z = z - (muz_n * dtau_correction);
@@ -248,6 +312,12 @@ static void walk(const oracle_params *P, draw_src *src, double wvl, double ssa_i
             }
         } else if (d.u_ssa >= ssa_event) {           /* MC3D:1461-1466 */
             condition = (ext_state == 1) ? 4 : 5;
+        }
+        if (src->use_philox && kind == EV_WALK) {
+            /* a photon that survives an event needing attention (boundary hit, possible absorption, or due for the
+             * GPU path's renormalisation: key16 >= min(t16, 0xffc0)) continues with the next group of its stream */
+            uint32_t thot = src->t16[species] < RENORM_KEY ? src->t16[species] : RENORM_KEY;
+            if (attention || src->key16 >= thot) src->slot = 4;
         }
     }
 
@@ -321,8 +391,8 @@ typedef struct {
 static int wavelength_row(const oracle_params *P, draw_src *src, int n_rows)
 {
     /* MC3D:1515-1520: wvls = np.around(np.random.normal(wvl0, scale), 2); Box-Muller on Philox uniforms */
-    uint32_t w[4];
-    philox_block(src, 0, TAG_WAVELENGTH, w);
+    uint32_t *w = src->first;
+    philox_block(src, 0, TAG_FIRST, w);
     double u1 = u32_to_unit(w[0]), u2 = u32_to_unit(w[1]);
     double zn = sqrt(-2.0 * log(u1)) * cos(TWO_PIE * u2);
     double k = rint((P->wvl0_um + P->sigma_um * zn) * 100.0);
@@ -349,8 +419,11 @@ static void *philox_worker(void *arg)
         src.key[0] = (uint32_t)J->seed; src.key[1] = (uint32_t)(J->seed >> 32);
         src.pid = J->begin + idx;
         src.impurity_on = impurity_on;
+        src.slot = 4;
         int row = wavelength_row(J->P, &src, J->n_rows);
         const oracle_row *R = &J->table[row];
+        threshold40(R->ssa_ice, &src.t16[0], &src.t24[0]);
+        threshold40(R->ssa_imp, &src.t16[1], &src.t24[1]);
         photon_out o;
         walk(J->P, &src, R->wvl_um, R->ssa_ice, R->ssa_imp, R->g, R->ext_cff_mss, R->p_ext_imp, &o);
         J->n_events += (uint64_t)(o.n_scat + 1);
@@ -411,6 +484,6 @@ int oracle_philox(const oracle_params *P, const oracle_row *table, int n_rows, u
 }
 
 /* exposed for unit tests */
-void oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) { philox4x32_10(ctr, key, out); }
+void oracle_philox4x32(int rounds, const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) { philox4x32(rounds, ctr, key, out); }
 double oracle_henyey_greenstein2(double g, double r) { return henyey_greenstein2(g, r); }
 int oracle_histogram_bin(double x, int n_bins, const double *edges) { return histogram_bin(x, n_bins, edges); }

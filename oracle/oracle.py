@@ -102,11 +102,12 @@ def philox(params, table, seed, begin, n, n_threads=1, fp32_angles=True, records
     return out
 
 
-def philox4x32_10(ctr, key):
+def philox4x32(ctr, key, rounds=7):
+    """Philox4x32-R block (the production stream uses R = 7; Random123's known answers exist for R = 7 and 10)."""
     ctr = np.ascontiguousarray(ctr, dtype=np.uint32)
     key = np.ascontiguousarray(key, dtype=np.uint32)
     out = np.zeros(4, np.uint32)
-    lib().oracle_philox4x32_10(_p(ctr), _p(key), _p(out))
+    lib().oracle_philox4x32(C.c_int(int(rounds)), _p(ctr), _p(key), _p(out))
     return out
 
 

@@ -1,4 +1,4 @@
-"""Production mode (fp32 walk, Philox4x32-10 keyed on (seed, photon id)) through the C ABI.
+"""Production mode (fp32 walk, Philox4x32-7 keyed on (seed, photon id)) through the C ABI.
 
 Parity is shown three ways:
   1. against the oracle's production-mode restatement fed the SAME Philox draws (fp64, reference arithmetic): per-photon
@@ -299,17 +299,18 @@ def test_results_do_not_depend_on_range_split_or_launch_shape():
             for col in ref:
                 assert np.array_equal(rec[col], ref[col]), (col, bps, bt, thr)
             assert np.array_equal(t, tref)
-        # (c) events per warp vote (walk_kernel's EPV template parameter; chosen automatically in production)
-        for epv in ('1', '2', '4'):
-            os.environ['MC3D_EVENTS_PER_VOTE'] = epv
+        # (c) the fused one-thread-per-photon kernel (chosen automatically for short walks) and the persistent
+        #     three-kernel path follow the same per-photon stream: bit-identical records
+        for path in ('fused', 'persistent'):
+            os.environ['MC3D_WALK_PATH'] = path
             try:
                 with engine.Context([0]) as c2:
-                    rec, t, _ = c2.run(P, rows, seed, 0, n)
+                    rec, t, st2 = c2.run(P, rows, seed, 0, n)
             finally:
-                del os.environ['MC3D_EVENTS_PER_VOTE']
+                del os.environ['MC3D_WALK_PATH']
             for col in ref:
-                assert np.array_equal(rec[col], ref[col]), (col, epv)
-            assert np.array_equal(t, tref)
+                assert np.array_equal(rec[col], ref[col]), (col, path)
+            assert np.array_equal(t, tref) and st2['n_events'] == st['n_events']
         # (d) drain-phase consolidation (photons handed between the warps of a block through shared memory; switched
         #     on automatically when other calls are in flight): any hand-over threshold, several grid shapes
         for give, bps in (('0', 255), ('8', 255), ('16', 1), ('24', 255), ('31', 2)):

@@ -42,13 +42,16 @@ def test_recorded_stream_accounting():
 
 
 def test_philox_known_answers():
-    # Random123 kat_vectors, philox4x32 10 rounds
-    kat = [([0, 0, 0, 0], [0, 0], [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]),
-           ([0xffffffff] * 4, [0xffffffff] * 2, [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]),
-           ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0],
-            [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1])]
-    for ctr, key, expect in kat:
-        assert oracle.philox4x32_10(ctr, key).tolist() == expect
+    # Random123 kat_vectors: philox4x32 with 7 rounds (the production stream) and with 10 rounds
+    pi_ctr, pi_key = [0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]
+    kat = [(7, [0, 0, 0, 0], [0, 0], [0x5f6fb709, 0x0d893f64, 0x4f121f81, 0x4f730a48]),
+           (7, [0xffffffff] * 4, [0xffffffff] * 2, [0x5207ddc2, 0x45165e59, 0x4d8ee751, 0x8c52f662]),
+           (7, pi_ctr, pi_key, [0x4dfccaba, 0x190a87f0, 0xc47362ba, 0xb6b5242a]),
+           (10, [0, 0, 0, 0], [0, 0], [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]),
+           (10, [0xffffffff] * 4, [0xffffffff] * 2, [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]),
+           (10, pi_ctr, pi_key, [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1])]
+    for rounds, ctr, key, expect in kat:
+        assert oracle.philox4x32(ctr, key, rounds).tolist() == expect
 
 
 def test_henyey_greenstein_inverse_cdf():
