@@ -19,7 +19,8 @@ after `warmup` untimed ones; the library slots are primed -- buffers allocated -
   value     outputs stay on the GPU except the 61 KB tally block per call; one NCCL reduce of the summed tallies at the
             end when N > 1 (the path's only collective).
   e2e       the same steps through the public C-ABI call with HOST buffers: inputs (SSP table, bin edges) uploaded from
-            pinned host memory and the packed per-photon records + tallies copied back to pinned host memory, every call.
+            pinned host memory and the per-photon records (packed, 16 B each) + tallies copied back to pinned host memory,
+            every call.
   isolated  single calls, one at a time (what a plain `MonteCarlo.run(10^6)` issues): CUDA-event duration per call.
 NVML clocks are sampled by a background thread only (never from the timing thread).
 
@@ -351,7 +352,7 @@ def main():
         events, total = pipeline(n_steps * calls, first_call, with_records)
         checksum = 0
         if with_records:                                  # read the step's result on the host
-            checksum = int(bufs[0].view(n)['n_scat'][:16].sum()) + int(total[:, 1].sum())
+            checksum = int((bufs[0].packed(n)[:16, 0] >> 9).sum()) + int(total[:, 1].sum())
         e1.record()
         e1.synchronize()
         t_dev, t_host = e0.elapsed_time(e1) * 1e-3, time.perf_counter() - t0
@@ -397,6 +398,28 @@ def main():
     stats = st
     events_total = reduce_ranks(float(events_a), dist.ReduceOp.SUM)
     events_total_e = reduce_ranks(float(events_e), dist.ReduceOp.SUM)
+
+    # ---- the box's device-to-host ceiling, all ranks copying at once (what bounds e2e): 16 MB copies into pinned memory
+    def d2h_ceiling(nbytes, reps=320):
+        src = torch.empty(nbytes, dtype=torch.uint8, device='cuda')
+        dsts = [torch.empty(nbytes, dtype=torch.uint8).pin_memory() for _ in range(4)]
+        streams = [torch.cuda.Stream() for _ in range(2)]
+
+        def go(k):
+            for r in range(k):
+                with torch.cuda.stream(streams[r % 2]):
+                    dsts[r % 4].copy_(src, non_blocking=True)
+            torch.cuda.synchronize()
+        go(8)
+        barrier()
+        t0 = time.perf_counter()
+        go(reps)
+        dt = time.perf_counter() - t0
+        barrier()
+        return nbytes * reps / dt / 1e9
+    link_gbps = d2h_ceiling(16 * n)
+    link_min = reduce_ranks(link_gbps, dist.ReduceOp.MIN)
+    link_sum = reduce_ranks(link_gbps, dist.ReduceOp.SUM)
 
     # ---- GPU-count invariance: photon ids [0, 10^6) split over the ranks (np.array_split boundaries, PAR:14-15),
     # records gathered in rank order (= photon order, PAR:19) + NCCL-reduced tally -> SHA-256.  Rank 0 also walks the
@@ -448,7 +471,7 @@ def main():
         except Exception:
             pass
         hbm_peak = peaks.get('hbm_gbs', 6650.0)
-        rec_bytes = engine.records_layout(n)[1]
+        rec_bytes = 16 * n                                     # packed records, include/mc3d.h
         traffic = NCU_TRAFFIC_BYTES_PER_PHOTON
         line = {
             'metric': 'photon_packets_per_s', 'value': world * n_calls * n / T_a, 'unit': 'photons/s',
@@ -470,7 +493,12 @@ def main():
                     'h2d_bytes_per_step': int(calls * (64 * n_rows + 8 * (P.n_theta_bins + 1 + max(1, P.n_phi_bins) + 1))),
                     'd2h_bytes_per_step': int(calls * (rec_bytes + tallies[0].nbytes + 24)),
                     'd2h_GBps_per_gpu': calls * (rec_bytes + tallies[0].nbytes + 24) * args.steps / T_e / 1e9,
-                    'record_bytes_per_photon': rec_bytes / float(n), 'host_checksum': checksum},
+                    'record_bytes_per_photon': rec_bytes / float(n), 'host_checksum': checksum,
+                    'link_GBps_per_gpu': link_min, 'link_GBps_aggregate': link_sum,
+                    'link_frac': calls * (rec_bytes + tallies[0].nbytes + 24) * args.steps / T_e / 1e9 / link_min,
+                    'link_is': 'device-to-host rate of 16 MB copies into pinned host memory measured in this run with all %d ranks '
+                               'copying at once (torch copy_, 2 streams): slowest rank / sum over ranks; link_frac = d2h_GBps_per_gpu / '
+                               'link_GBps_per_gpu' % world},
             'consistency': {'e2e_le_value': bool(T_e >= 0.98 * T_a)},
             'invariance_digest': digest,
             'invariance_is': 'SHA-256 of the six record columns of photon ids [0, %d) gathered in rank order + the NCCL-reduced tally '

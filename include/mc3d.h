@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define MC3D_ABI_VERSION 1
+#define MC3D_ABI_VERSION 2
 
 /* error codes */
 #define MC3D_OK 0
@@ -78,7 +78,15 @@ typedef struct mc3d_ssp_row {
 
 /* Per-photon outcome records, struct of arrays, index = photon id - photon_begin.  Any pointer may be NULL
  * (that column is then not copied back).  Replaces the list of tuples returned through comm.gather
- * (monte_carlo3D.py:1487-1488, 1618); wvn and snow_depth are table[wvl_row].  */
+ * (monte_carlo3D.py:1487-1488, 1618); wvn and snow_depth are table[wvl_row].
+ *
+ * `packed` (optional) selects the 16-byte packed record instead of the six columns (19 bytes): when it is non-NULL
+ * the columns are ignored and photon p's record is the four 32-bit words packed[4p .. 4p+3]
+ *     word 0   n_scat << 9 | wvl_row      (n_scat saturates at MC3D_PACKED_NSCAT_MAX; tables of <= 512 rows only)
+ *     word 1   float bits of theta_n,     sign bit = condition bit 0
+ *     word 2   float bits of phi_n,       sign bit = condition bit 1
+ *     word 3   float bits of path_length, sign bit = condition bit 2      (the three floats are never negative)
+ * -- one copy of 16 bytes per photon over PCIe; mc3d_unpack_records expands it into columns on the host. */
 typedef struct mc3d_records {
     uint8_t *condition;  /* 1..5                                                                           */
     int16_t *wvl_row;    /* row of the SSP table                                                            */
@@ -86,7 +94,11 @@ typedef struct mc3d_records {
     float *phi_n;        /* [0, 2 pi), 0 for an unscattered photon                                          */
     uint32_t *n_scat;    /* i - 1                                                                           */
     float *path_length;  /* metres inside the slab                                                          */
+    uint32_t *packed;    /* NULL, or uint32[4 * n_photon]: the packed form (see above)                      */
 } mc3d_records;
+#define MC3D_PACKED_MAX_ROWS 512
+#define MC3D_PACKED_NSCAT_MAX 0x7fffffu /* a photon with more scatterings is stored with this value and the call's
+                                           mc3d_stats.packed_saturated is set                                */
 
 /* Same, fp64, for replay mode (bit-for-bit comparable with the reference's tuples). */
 typedef struct mc3d_records_f64 {
@@ -110,7 +122,7 @@ typedef struct mc3d_stats {
     int32_t sm_clock_khz; /* cudaDevAttrClockRate of device 0                                               */
     int32_t grid_blocks;  /* persistent blocks launched per device                                          */
     int32_t block_threads;
-    int32_t reserved;
+    int32_t packed_saturated; /* 1 if a photon's n_scat exceeded MC3D_PACKED_NSCAT_MAX in a packed-record call */
 } mc3d_stats;
 
 /* Optional histograms of two per-photon columns, binned on the GPU so that no records have to leave it
@@ -158,7 +170,7 @@ int mc3d_host_free(void *ptr);
 int mc3d_records_layout(uint64_t n_photon, uint64_t offsets[6], uint64_t *total_bytes);
 
 /* ---- the hot path --------------------------------------------------------------------------------------
- * Production mode (fp32 walk, Philox4x32-10 keyed on (seed, photon id)).  Walks photon ids
+ * Production mode (fp32 walk, Philox4x32-7 keyed on (seed, photon id)).  Walks photon ids
  * [photon_begin, photon_begin + n_photon) -- replaces the loop monte_carlo3D.py:1613-1616 together with
  * initial_pdfs/populate_pdfs (monte_carlo3D.py:885-921, 1010-1044), Henyey_Greenstein2 (790-800) and the
  * per-photon wavelength draw (1515-1520).  In a multi-device context the range is split with np.array_split
@@ -183,7 +195,8 @@ int mc3d_run(mc3d_ctx *ctx, const mc3d_params *params, const mc3d_ssp_row *table
  * and tally buffers must stay valid (and should be pinned) until mc3d_wait.  `slot` (0 .. MC3D_N_SLOTS-1) selects one
  * of sixteen independent device buffer sets, each with its own stream, so that several calls can be in flight: the
  * long-walk tail and the copy-back of one call overlap the walks of the next ones.  mc3d_wait(ctx, slot, stats)
- * blocks until that slot is complete. */
+ * blocks until that slot is complete and returns the call's statistics (the `stats` of mc3d_run_async, if not NULL,
+ * is only zeroed: nothing has run yet when it returns). */
 int mc3d_run_async(mc3d_ctx *ctx, int slot, const mc3d_params *params, const mc3d_ssp_row *table, int n_rows,
                    uint64_t seed, uint64_t photon_begin, uint64_t n_photon, const mc3d_records *records,
                    uint64_t *tally, mc3d_stats *stats);
@@ -222,6 +235,9 @@ int mc3d_replay(mc3d_ctx *ctx, const mc3d_params *params, uint64_t n_photon, con
 int64_t mc3d_write_records_text(const char *path, int append, uint64_t n, const uint8_t *condition, const int16_t *wvl_row,
                                 const float *theta_n, const float *phi_n, const uint32_t *n_scat, const float *path_length,
                                 const double *wvn_by_row, const double *snow_depth_by_row, int n_rows, int n_threads);
+/* Host code: expand n packed records (mc3d_records.packed layout) into the columns of `out` (any may be NULL;
+ * out->packed is ignored).  n_threads <= 0 uses every host core. */
+int mc3d_unpack_records(const uint32_t *packed, uint64_t n, const mc3d_records *out, int n_threads);
 /* CPython repr(x) of one double into buf (at least 32 bytes, NUL-terminated); returns its length. */
 int mc3d_py_repr(double x, char *buf);
 

@@ -67,13 +67,19 @@ __global__ void __launch_bounds__(BLOCK) finalize_kernel(const __grid_constant__
             phi = atan2f(a.y, a.x);
             if (phi < 0.0f) phi += 6.283185307179586f;
         }
-        if (P.condition) P.condition[p] = (uint8_t)cond;
-        if (P.wvl_row) P.wvl_row[p] = (int16_t)row;
-        if (P.theta_n) P.theta_n[p] = theta;
-        if (P.phi_n) P.phi_n[p] = phi;
-        if (P.n_scat) P.n_scat[p] = b.x;
-        const float path_m = a.w * inv_ext[row];
-        if (P.path_length) P.path_length[p] = path_m;
+        // fp32 rounding can leave a path of (nearly) zero length slightly negative (Lambertian surface, immediate exit)
+        const float path_m = fmaxf(a.w * inv_ext[row], 0.0f);
+        if (P.packed) {
+            P.packed[p] = make_uint4((min(b.x, 0x7fffffu) << 9) | row, __float_as_uint(theta) | (cond << 31),
+                                     __float_as_uint(phi) | ((cond >> 1) << 31), __float_as_uint(path_m) | ((cond >> 2) << 31));
+        } else {
+            if (P.condition) P.condition[p] = (uint8_t)cond;
+            if (P.wvl_row) P.wvl_row[p] = (int16_t)row;
+            if (P.theta_n) P.theta_n[p] = theta;
+            if (P.phi_n) P.phi_n[p] = phi;
+            if (P.n_scat) P.n_scat[p] = b.x;
+            if (P.path_length) P.path_length[p] = path_m;
+        }
         events += (unsigned long long)b.x + 1ull;
         ns_min = min(ns_min, b.x);
         ns_max = max(ns_max, b.x);

@@ -122,6 +122,31 @@ void format_range(uint64_t lo, uint64_t hi, const uint8_t *condition, const int1
 
 extern "C" {
 
+// Expand packed 16-byte records (mc3d_records.packed in include/mc3d.h) into columns.  Host code, threads over ranges.
+int mc3d_unpack_records(const uint32_t *packed, uint64_t n, const mc3d_records *out, int n_threads)
+{
+    if (!out || (n && !packed)) return MC3D_EINVAL;
+    if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    n_threads = (int)std::min<uint64_t>((uint64_t)n_threads, std::max<uint64_t>(1, n >> 16));
+    auto work = [&](uint64_t lo, uint64_t hi) {
+        for (uint64_t k = lo; k < hi; ++k) {
+            const uint32_t m = packed[4 * k], t = packed[4 * k + 1], f = packed[4 * k + 2], l = packed[4 * k + 3];
+            if (out->condition) out->condition[k] = (uint8_t)((t >> 31) | ((f >> 31) << 1) | ((l >> 31) << 2));
+            if (out->wvl_row) out->wvl_row[k] = (int16_t)(m & 0x1ffu);
+            if (out->n_scat) out->n_scat[k] = m >> 9;
+            const uint32_t tb = t & 0x7fffffffu, fb = f & 0x7fffffffu, lb = l & 0x7fffffffu;
+            if (out->theta_n) memcpy(&out->theta_n[k], &tb, 4);
+            if (out->phi_n) memcpy(&out->phi_n[k], &fb, 4);
+            if (out->path_length) memcpy(&out->path_length[k], &lb, 4);
+        }
+    };
+    if (n_threads <= 1) { work(0, n); return MC3D_OK; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; ++t) th.emplace_back(work, n * t / n_threads, n * (t + 1) / n_threads);
+    for (auto &t : th) t.join();
+    return MC3D_OK;
+}
+
 // repr(x) of one double into buf (>= 32 bytes); returns the length.  For tests.
 int mc3d_py_repr(double x, char *buf)
 {

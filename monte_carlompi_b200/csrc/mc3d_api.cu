@@ -157,6 +157,7 @@ struct Slot {
     size_t tally_len = 0;
     int n_chunks = 0;
     uint64_t *user_tally = nullptr;
+    bool packed = false;                    // the pending call returns packed records
 };
 
 struct Device {
@@ -186,6 +187,7 @@ struct mc3d_ctx {
     bool done_hist[N_SLOTS] = {};
     mc3d_extrema done_extrema[N_SLOTS]{};
     std::vector<uint64_t> done_counts[N_SLOTS];
+    DevBuf<unsigned long long> reduce_buf;   // mc3d_reduce_tally's device staging (multi-rank contexts)
 };
 
 // ------------------------------------------------------------------------------------------------ helpers
@@ -415,6 +417,7 @@ int mc3d_destroy(mc3d_ctx *ctx)
     if (!ctx) return MC3D_OK;
     for (size_t k = 0; k < ctx->comms.size(); ++k)
         if (ctx->comms[k] && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comms[k]);
+    if (ctx->reduce_buf.p && !ctx->devs.empty() && cudaSetDevice(ctx->devs[0].id) == cudaSuccess) ctx->reduce_buf.release();
     for (Device &d : ctx->devs) {
         if (cudaSetDevice(d.id) != cudaSuccess) continue;
         for (Slot &s : d.slot) {
@@ -503,7 +506,7 @@ int mc3d_run_async(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, const mc3d
                    uint64_t seed, uint64_t photon_begin, uint64_t n_photon, const mc3d_records *rec,
                    uint64_t *tally, mc3d_stats *stats)
 {
-    (void)stats;
+    if (stats) memset(stats, 0, sizeof *stats);   // filled by mc3d_wait (the call has not run yet)
     int rc = check_ctx(ctx);
     if (rc) return rc;
     if (slot_idx < 0 || slot_idx >= N_SLOTS) return fail(MC3D_EINVAL, "slot must be in [0, %d)", N_SLOTS);
@@ -619,12 +622,16 @@ static int run_async_impl(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, con
             CUDA_TRY(cudaHostAlloc((void **)&s.host_acc, acc_copy * sizeof(unsigned long long), cudaHostAllocPortable));
             s.host_acc_cap = acc_copy;
         }
-        const bool want_rec = rec != nullptr && cnt != 0;
+        const bool want_packed = rec != nullptr && rec->packed != nullptr && cnt != 0;
+        if (want_packed && n_rows > MC3D_PACKED_MAX_ROWS)
+            return fail(MC3D_EINVAL, "packed records support tables of <= %d rows (got %d): use the record columns", MC3D_PACKED_MAX_ROWS, n_rows);
+        const bool want_rec = rec != nullptr && cnt != 0 && !want_packed;
         void *const host_col[6] = {rec ? (void *)rec->condition : nullptr, rec ? (void *)rec->wvl_row : nullptr,
                                    rec ? (void *)rec->theta_n : nullptr,   rec ? (void *)rec->phi_n : nullptr,
                                    rec ? (void *)rec->n_scat : nullptr,    rec ? (void *)rec->path_length : nullptr};
         size_t rec_off[6];
         if (want_rec) CUDA_TRY(s.recs.ensure(records_layout(chunk_cap, rec_off)));
+        if (want_packed) CUDA_TRY(s.recs.ensure((size_t)chunk_cap * 16));
         // one copy instead of six when the caller's arrays sit in one block packed like the device's
         bool packed_host = want_rec && n_dev == 1 && n_chunks == 1;
         if (packed_host) {
@@ -723,6 +730,7 @@ static int run_async_impl(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, con
                 F.n_scat = host_col[4] ? reinterpret_cast<uint32_t *>(s.recs.p + rec_off[4]) : nullptr;
                 F.path_length = host_col[5] ? reinterpret_cast<float *>(s.recs.p + rec_off[5]) : nullptr;
             }
+            if (want_packed) F.packed = reinterpret_cast<uint4 *>(s.recs.p);
             F.tally = d_tally;
             F.n_events = d_tally + tally_len;
             F.extrema = reinterpret_cast<uint32_t *>(d_extras);
@@ -735,7 +743,9 @@ static int run_async_impl(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, con
             }
             CUDA_TRY(launch_finalize(F, d.sm_count, s.stream));
             CUDA_TRY(cudaEventRecord(s.ev[2 * c + 1], s.stream));
-            if (packed_host) {
+            if (want_packed) {
+                CUDA_TRY(cudaMemcpyAsync(rec->packed + 4 * (off + c_off), s.recs.p, (size_t)c_cnt * 16, cudaMemcpyDeviceToHost, s.stream));
+            } else if (packed_host) {
                 CUDA_TRY(cudaMemcpyAsync(host_col[0], s.recs.p, rec_off[5] + (size_t)c_cnt * REC_ITEM[5], cudaMemcpyDeviceToHost, s.stream));
             } else if (want_rec) {
                 const uint64_t o = off + c_off;   // this chunk's first photon in the caller's arrays
@@ -752,6 +762,7 @@ static int run_async_impl(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, con
         s.tally_len = tally_len;
         s.n_chunks = n_chunks;
         s.user_tally = tally;
+        s.packed = want_packed;
     }
 
     // ---- the only collective: sum the tally blocks of all devices of this process onto device 0 (NVLink)
@@ -819,6 +830,7 @@ int mc3d_wait(mc3d_ctx *ctx, int slot_idx, mc3d_stats *stats)
         mc3d_extrema &x = ctx->done_extrema[slot_idx];
         if (e[0] > e[1]) { e[0] = e[1] = 0u; e[2] = e[3] = 0u; }   // no photons
         x.n_scat_min = e[0]; x.n_scat_max = e[1];
+        st.packed_saturated = (ctx->devs[0].slot[slot_idx].packed && e[1] > MC3D_PACKED_NSCAT_MAX) ? 1 : 0;
         memcpy(&x.path_min, &e[2], 4); memcpy(&x.path_max, &e[3], 4);
     }
     Slot &s0 = ctx->devs[0].slot[slot_idx];
@@ -884,15 +896,14 @@ int mc3d_reduce_tally(mc3d_ctx *ctx, uint64_t *tally, uint64_t n, int root)
     Device &d = ctx->devs[0];
     cudaStream_t stream0 = d.slot[0].stream;
     CUDA_TRY(cudaSetDevice(d.id));
-    unsigned long long *buf = nullptr;
-    CUDA_TRY(cudaMalloc((void **)&buf, std::max<uint64_t>(n, 1) * sizeof(unsigned long long)));
+    CUDA_TRY(ctx->reduce_buf.ensure(std::max<uint64_t>(n, 1)));   // kept by the context: no allocation per call
+    unsigned long long *buf = ctx->reduce_buf.p;
     cudaError_t e = cudaMemcpyAsync(buf, tally, n * sizeof(uint64_t), cudaMemcpyHostToDevice, stream0);
     ncclResult_t r = ncclSuccess;
     if (e == cudaSuccess) r = g_nccl.Reduce(buf, buf, n, ncclUint64, ncclSum, root, ctx->comms[0], stream0);
     if (e == cudaSuccess && r == ncclSuccess && ctx->rank == root)
         e = cudaMemcpyAsync(tally, buf, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, stream0);
     cudaError_t e2 = cudaStreamSynchronize(stream0);
-    cudaFree(buf);
     if (r != ncclSuccess) return fail(MC3D_ENCCL, "ncclReduce failed: %s", g_nccl.GetErrorString(r));
     if (e != cudaSuccess) return fail(MC3D_ECUDA, "tally copy failed: %s", cudaGetErrorString(e));
     if (e2 != cudaSuccess) return fail(MC3D_ECUDA, "stream sync failed: %s", cudaGetErrorString(e2));

@@ -125,6 +125,7 @@ struct FinalizeParams {
     float *phi_n;
     uint32_t *n_scat;
     float *path_length;
+    uint4 *packed;               // 16-byte packed records (mc3d_records.packed) instead of the columns, or null
     unsigned long long *tally;   // [n_rows][N_COND + n_theta_bins * max(1, n_phi_bins)] or null
     unsigned long long *n_events;
     // optional n_scat / path-length histograms (mc3d_hist_spec) and the always-on extrema

@@ -15,12 +15,15 @@ N_COND = 8
 N_SLOTS = 16
 FLAG_LAMBERT_BOTTOM = 1
 FLAG_LAMBERT_SURFACE = 2
-ABI_VERSION = 1
+ABI_VERSION = 2
+PACKED_MAX_ROWS = 512          # packed 16-byte records hold the SSP row in 9 bits
+PACKED_NSCAT_MAX = 0x7fffff    # ... and n_scat in 23 bits (saturating; Stats.packed_saturated reports it)
 
 EXPORTS = ('mc3d_abi_version', 'mc3d_last_error', 'mc3d_query', 'mc3d_create', 'mc3d_nccl_unique_id',
            'mc3d_create_rank', 'mc3d_destroy', 'mc3d_host_alloc', 'mc3d_host_free', 'mc3d_run', 'mc3d_run_async',
            'mc3d_wait', 'mc3d_reduce_tally', 'mc3d_replay', 'mc3d_set_launch', 'mc3d_write_records_text', 'mc3d_py_repr',
-           'mc3d_set_histograms', 'mc3d_get_histograms', 'mc3d_records_layout', 'mc3d_set_input_caching')
+           'mc3d_set_histograms', 'mc3d_get_histograms', 'mc3d_records_layout', 'mc3d_set_input_caching',
+           'mc3d_unpack_records')
 
 
 class Mc3dError(RuntimeError):
@@ -41,7 +44,7 @@ class Params(C.Structure):
 
 class Records(C.Structure):
     _fields_ = [('condition', C.c_void_p), ('wvl_row', C.c_void_p), ('theta_n', C.c_void_p),
-                ('phi_n', C.c_void_p), ('n_scat', C.c_void_p), ('path_length', C.c_void_p)]
+                ('phi_n', C.c_void_p), ('n_scat', C.c_void_p), ('path_length', C.c_void_p), ('packed', C.c_void_p)]
 
 
 class RecordsF64(C.Structure):
@@ -54,10 +57,10 @@ class Stats(C.Structure):
     _fields_ = [('n_photon', C.c_uint64), ('n_events', C.c_uint64), ('kernel_ms', C.c_double),
                 ('total_ms', C.c_double), ('n_devices', C.c_int32), ('sm_count', C.c_int32),
                 ('sm_clock_khz', C.c_int32), ('grid_blocks', C.c_int32), ('block_threads', C.c_int32),
-                ('reserved', C.c_int32)]
+                ('packed_saturated', C.c_int32)]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_ if k != 'reserved'}
+        return {k: getattr(self, k) for k, _ in self._fields_}
 
 
 class HistSpec(C.Structure):
@@ -112,6 +115,7 @@ def load_library():
     lib.mc3d_records_layout.argtypes = [u64, vp, vp]
     lib.mc3d_set_input_caching.argtypes = [vp, i32]
     lib.mc3d_get_histograms.argtypes = [vp, i32, vp, vp, vp]
+    lib.mc3d_unpack_records.argtypes = [vp, u64, vp, i32]
     if lib.mc3d_abi_version() != ABI_VERSION:
         raise Mc3dError('libmc3d.so ABI %d != expected %d' % (lib.mc3d_abi_version(), ABI_VERSION))
     _lib = lib
@@ -205,7 +209,7 @@ class PinnedArray(object):
 
 
 def records_layout(n):
-    """(byte offsets of the six record columns, total bytes) of the packed block for an n-photon call
+    """(byte offsets of the six record columns, total bytes) of the column block for an n-photon call
     (mc3d_records_layout): record arrays laid out like this come back with one device-to-host copy."""
     off = (C.c_uint64 * 6)()
     total = C.c_uint64(0)
@@ -213,39 +217,39 @@ def records_layout(n):
     return [int(x) for x in off], int(total.value)
 
 
+def unpack_records(packed, n=None, n_threads=0):
+    """Expand packed 16-byte records (uint32 array, 4 words per photon; mc3d_records.packed) into a dict of columns."""
+    packed = np.ascontiguousarray(packed, dtype=np.uint32).reshape(-1)
+    n = packed.size // 4 if n is None else int(n)
+    cols = {name: np.empty(n, dtype=dt) for name, dt in RECORD_COLUMNS}
+    out = Records(*[cols[name].ctypes.data for name, _ in RECORD_COLUMNS], None)
+    _check(load_library().mc3d_unpack_records(_ptr(packed), n, C.byref(out), int(n_threads)))
+    return cols
+
+
 class RecordBuffers(object):
-    """Pinned SoA record columns for up to ``capacity`` photons, in one block packed the way the library packs them
-    on the device (so an n-photon call returns its records with a single copy)."""
+    """Pinned destination for the records of up to ``capacity`` photons in the packed 16-byte form (one device-to-host
+    copy of 16 B per photon, include/mc3d.h); ``view(n)`` expands the first n into the six columns."""
 
     def __init__(self, capacity):
         self.capacity = int(capacity)
-        _, total = records_layout(self.capacity)
-        self._block = PinnedArray(max(total, 1), np.uint8)
-        self._views = {}
-
-    def _layout(self, n):
-        n = int(n)
-        if n > self.capacity:
-            raise ValueError('%d photons do not fit in RecordBuffers(%d)' % (n, self.capacity))
-        if n not in self._views:
-            off, _ = records_layout(n)
-            base = self._block.array
-            cols = {name: base[o:o + n * np.dtype(dt).itemsize].view(dt) for (name, dt), o in zip(RECORD_COLUMNS, off)}
-            ptrs = Records(*[base.ctypes.data + o for o in off])
-            if len(self._views) > 8:
-                self._views.clear()
-            self._views[n] = (cols, ptrs)
-        return self._views[n]
+        self._block = PinnedArray(max(4 * self.capacity, 4), np.uint32)
 
     def struct_for(self, n):
-        """mc3d_records pointing at the packed columns of an n-photon call."""
-        return self._layout(n)[1]
+        """mc3d_records asking for the packed records of an n-photon call."""
+        if int(n) > self.capacity:
+            raise ValueError('%d photons do not fit in RecordBuffers(%d)' % (n, self.capacity))
+        return Records(None, None, None, None, None, None, self._block.array.ctypes.data)
+
+    def packed(self, n):
+        """uint32 view (n, 4) of the packed records."""
+        return self._block.array[:4 * int(n)].reshape(int(n), 4)
 
     def view(self, n):
-        return dict(self._layout(n)[0])
+        """The first n records as a dict of (freshly unpacked) numpy columns."""
+        return unpack_records(self._block.array, int(n))
 
     def free(self):
-        self._views = {}
         self._block.free()
 
 
@@ -335,9 +339,12 @@ class Context(object):
         rec_struct = None
         if isinstance(records, RecordBuffers):
             rec_struct = records.struct_for(n_photon)
+        elif isinstance(records, np.ndarray):      # packed records into a caller-owned uint32 array
+            assert records.dtype == np.uint32 and records.flags.c_contiguous and records.size >= 4 * int(n_photon)
+            rec_struct = Records(None, None, None, None, None, None, records.ctypes.data)
         elif records is not None:
             rec_struct = Records(*[records[name].ctypes.data if records.get(name) is not None else None
-                                   for name, _ in RECORD_COLUMNS])
+                                   for name, _ in RECORD_COLUMNS], None)
         if tally is not None:
             assert tally.dtype == np.uint64 and tally.flags.c_contiguous
             assert tally.size == len(table) * params.tally_width
@@ -357,11 +364,18 @@ class Context(object):
         Returns (records dict or None, tally array or None, stats dict)."""
         table = np.ascontiguousarray(table, dtype=ROW_DTYPE)
         rec = None
-        if records:
+        packed = bool(records) and len(table) <= PACKED_MAX_ROWS and records != 'columns'
+        if packed:
+            rec = np.empty(4 * max(int(n_photon), 1), np.uint32)
+        elif records:
             rec = {name: np.empty(n_photon, dtype=dt) for name, dt in RECORD_COLUMNS}
         t = np.zeros((len(table), params.tally_width), np.uint64) if tally else None
         self.run_async(0, params, table, seed, photon_begin, n_photon, rec, t)
         stats = self.wait(0)
+        if packed:
+            if stats['packed_saturated']:      # a walk longer than 2^23 events: fetch the columns instead
+                return self.run(params, table, seed, photon_begin, n_photon, records='columns', tally=tally)
+            rec = unpack_records(rec, n_photon)
         return rec, t, stats
 
     def reduce_tally(self, tally, root=0):

@@ -223,15 +223,8 @@ class MonteCarlo(object):
             par = self._parallel = Parallel(n_photon, devices=self.devices)
         begin, count = par._map(n_photon)
         ctx = par.open()
-        # record columns land in page-locked host memory (copy-back at PCIe speed); the buffers are kept for reuse
-        if self._rec_buf is None or self._rec_buf.capacity < count:
-            if self._rec_buf is not None:
-                self._rec_buf.free()
-            self._rec_buf = engine.RecordBuffers(max(count, 1))
         tally = np.zeros((len(table), params.tally_width), np.uint64)
-        ctx.run_async(0, params, table, self.last_seed, begin, count, self._rec_buf, tally)
-        stats = ctx.wait(0)
-        records = {name: col.copy() for name, col in self._rec_buf.view(count).items()}
+        records, stats = self._walk_records(ctx, params, table, self.last_seed, begin, count, tally)
         if par.size > 1:
             ctx.reduce_tally(tally, root=0)
         self.last_table, self.last_stats = table, stats
@@ -251,6 +244,23 @@ class MonteCarlo(object):
             if write_output == 'binary':
                 output_file = sidecar
         print('%s' % output_file)   # for easy post processing
+
+    def _walk_records(self, ctx, params, table, seed, begin, count, tally):
+        """One synchronous walk returning (record columns, stats).  The records come back packed (16 B per photon) into
+        page-locked host memory -- copy-back at PCIe speed; the buffer is kept for reuse -- and are expanded on the
+        host; tables beyond the packed format's 512 rows, or a walk beyond its 2^23 scatterings, take the columns."""
+        if len(table) <= engine.PACKED_MAX_ROWS:
+            if self._rec_buf is None or self._rec_buf.capacity < count:
+                if self._rec_buf is not None:
+                    self._rec_buf.free()
+                self._rec_buf = engine.RecordBuffers(max(count, 1))
+            ctx.run_async(0, params, table, seed, begin, count, self._rec_buf, tally)
+            stats = ctx.wait(0)
+            if not stats['packed_saturated']:
+                return self._rec_buf.view(count), stats
+        records = {name: np.empty(count, dtype=dt) for name, dt in engine.RECORD_COLUMNS}
+        ctx.run_async(0, params, table, seed, begin, count, records, tally)
+        return records, ctx.wait(0)
 
     # ---- batched sweeps (reference monte_carlo3D-run.py:60-96, 112-122: one run() per wavelength / grain size) -----
     def run_sweep(self, cases, write_output=True, seed=None):
@@ -281,7 +291,7 @@ class MonteCarlo(object):
         def finish(slot):
             k, c, table, tally, n, r_eff, dirs = pending[slot]
             stats = ctx.wait(slot)
-            rec = {name: col.copy() for name, col in bufs[slot].view(n).items()}
+            rec = bufs[slot].view(n)
             depth_m = ssp.snow_depth(table, self.tau_tot, self.rho_snw)
             self.last_records, self.last_tally, self.last_table, self.last_stats = rec, tally, table, stats
             if write_output:

@@ -368,6 +368,27 @@ def test_long_visible_walks():
     assert abs(ratio.mean() - 1.0) < 0.02
 
 
+def test_packed_records_equal_the_columns():
+    # the 16-byte packed record (the default way records come back) against the six-column form, incl. every condition
+    rows = gpu_util.fixture_table('spectral', 100, 104, 156, 1e-5)
+    P, _ = gpu_util.both_params(30., 3.0, 0.5, 1.3, SIGMA13, 104, True)
+    ctx = gpu_util.context()
+    n = 300000
+    a, ta, _ = ctx.run(P, rows, 17, 5, n)
+    b, tb, _ = ctx.run(P, rows, 17, 5, n, records='columns')
+    assert set(np.unique(a['condition'])) == {1, 2, 3, 4, 5}
+    for col in a:
+        assert a[col].dtype == b[col].dtype and np.array_equal(a[col], b[col]), col
+    assert np.array_equal(ta, tb)
+    big = np.zeros(engine.PACKED_MAX_ROWS + 1, engine.ROW_DTYPE)      # more rows than the packed form can index
+    big[:] = rows[0]
+    Pb, _ = gpu_util.both_params(30., 3.0, 0.5, 1.3, 0.0, 130 - 256, True)
+    with pytest.raises(engine.Mc3dError):
+        ctx.run_async(0, Pb, big, 1, 0, 10, engine.RecordBuffers(10), None)
+    rec, _, _ = ctx.run(Pb, big, 1, 0, 1000)                            # ctx.run falls back to the columns by itself
+    assert (rec['wvl_row'] == 256).all()
+
+
 def test_argument_validation():
     rows = gpu_util.const_table(0.9, 0.75)
     ctx = gpu_util.context()

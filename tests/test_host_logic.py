@@ -308,3 +308,29 @@ def test_brf_and_albedo_from_tallies_match_per_photon_formulas():
     assert abs(fr[1] - (rec['condition'] == 1).mean()) < 1e-15 and abs(sum(fr.values()) - 1) < 1e-12
     # a Lambertian reflector has BRF == albedo in every bin (cos-law sampling above): check the normalisation
     assert abs(np.median(brf_t) - q_up) < 0.02
+
+
+def test_packed_records_unpack_on_the_host():
+    # include/mc3d.h: word 0 = n_scat << 9 | row, words 1..3 = float bits of theta, phi, path with the three condition
+    # bits in their sign bits; mc3d_unpack_records is host code (no GPU needed)
+    from monte_carlompi_b200 import engine
+    rng = np.random.RandomState(5)
+    n = 200000
+    cond = rng.randint(1, 6, n).astype(np.uint8)
+    row = rng.randint(0, 512, n).astype(np.int16)
+    n_scat = rng.randint(0, engine.PACKED_NSCAT_MAX + 1, n).astype(np.uint32)
+    theta = rng.uniform(0, np.pi, n).astype(np.float32)
+    phi = rng.uniform(0, 2 * np.pi, n).astype(np.float32)
+    phi[::7] = 0.0
+    path = rng.exponential(0.01, n).astype(np.float32)
+    packed = np.empty((n, 4), np.uint32)
+    packed[:, 0] = (n_scat << 9) | row.astype(np.uint32)
+    packed[:, 1] = theta.view(np.uint32) | ((cond.astype(np.uint32) & 1) << 31)
+    packed[:, 2] = phi.view(np.uint32) | (((cond.astype(np.uint32) >> 1) & 1) << 31)
+    packed[:, 3] = path.view(np.uint32) | (((cond.astype(np.uint32) >> 2) & 1) << 31)
+    for threads in (1, 0):
+        out = engine.unpack_records(packed, n, n_threads=threads)
+        for name, want in (('condition', cond), ('wvl_row', row), ('n_scat', n_scat), ('theta_n', theta), ('phi_n', phi),
+                           ('path_length', path)):
+            assert out[name].dtype == want.dtype and np.array_equal(out[name], want), name
+    assert engine.unpack_records(np.zeros(0, np.uint32))['condition'].size == 0
