@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define MC3D_ABI_VERSION 2
+#define MC3D_ABI_VERSION 3
 
 /* error codes */
 #define MC3D_OK 0
@@ -123,6 +123,8 @@ typedef struct mc3d_stats {
     int32_t grid_blocks;  /* persistent blocks launched per device                                          */
     int32_t block_threads;
     int32_t packed_saturated; /* 1 if a photon's n_scat exceeded MC3D_PACKED_NSCAT_MAX in a packed-record call */
+    int32_t walk_path;    /* MC3D_PATH_FUSED or MC3D_PATH_PERSISTENT: the kernels that ran                   */
+    int32_t reserved;
 } mc3d_stats;
 
 /* Optional histograms of two per-photon columns, binned on the GPU so that no records have to leave it
@@ -202,6 +204,35 @@ int mc3d_run_async(mc3d_ctx *ctx, int slot, const mc3d_params *params, const mc3
                    uint64_t *tally, mc3d_stats *stats);
 int mc3d_wait(mc3d_ctx *ctx, int slot, mc3d_stats *stats);
 
+/* ---- sweeps: many cases, the same launches --------------------------------------------------------------------
+ * The reference's driver loops MonteCarlo.run over wavelengths, grain radii and zenith angles (monte_carlo3D-run.py:
+ * 60-96, 112-122), one full run each.  mc3d_run_sweep walks all the cases of such a loop together: one concatenated
+ * SSP table, one set of launches over the concatenated photons, so that short cases share the GPU with long ones and
+ * small cases do not pay a launch (and its tail) each.
+ *
+ * Case c owns rows table[row_begin .. row_begin + n_rows) and n_photon photons; its photon j is photon id
+ * (c << 40) + j of the stream `seed` -- the case index sits in the high bits of the Philox counter -- so the call
+ * equals, bit for bit, n_cases calls mc3d_run(&cases[c].params, table + row_begin, n_rows, seed, (uint64_t)c << 40,
+ * n_photon, ...) with their records concatenated in case order (wvl_row counts from the case's row_begin) and their
+ * tallies stacked by table row: tally is uint64[n_rows_total * (MC3D_N_COND + n_theta_bins * max(1, n_phi_bins))].
+ * Cases may share rows only as identical ranges with equal tau_tot and rho_snw (typically: one table, several
+ * zenith angles); n_theta_bins / n_phi_bins are common to all cases.  case_events (NULL or uint64[n_cases]) receives
+ * the events of each case.  The asynchronous form takes a slot like mc3d_run_async (finish with mc3d_wait) and a
+ * sub-range [range_begin, range_begin + range_count) of the concatenated photons, which is how ranks of a multi-rank
+ * context share a sweep (records are indexed from range_begin; tallies and case_events cover the sub-range). */
+typedef struct mc3d_sweep_case {
+    mc3d_params params;
+    int32_t row_begin;
+    int32_t n_rows;
+    uint64_t n_photon;   /* < 2^40 */
+} mc3d_sweep_case;
+#define MC3D_SWEEP_MAX_CASES 1024
+int mc3d_run_sweep(mc3d_ctx *ctx, const mc3d_sweep_case *cases, int n_cases, const mc3d_ssp_row *table, int n_rows_total,
+                   uint64_t seed, const mc3d_records *records, uint64_t *tally, uint64_t *case_events, mc3d_stats *stats);
+int mc3d_run_sweep_async(mc3d_ctx *ctx, int slot, const mc3d_sweep_case *cases, int n_cases, const mc3d_ssp_row *table,
+                         int n_rows_total, uint64_t seed, uint64_t range_begin, uint64_t range_count,
+                         const mc3d_records *records, uint64_t *tally, uint64_t *case_events);
+
 /* Sum `tally` (uint64[n]) over the ranks of a multi-rank context with one ncclReduce to `root`
  * (replaces comm.gather for the reduced quantities, parallelize.py:19).  In place; no-op for world_size 1. */
 int mc3d_reduce_tally(mc3d_ctx *ctx, uint64_t *tally, uint64_t n, int root);
@@ -245,6 +276,16 @@ int mc3d_py_repr(double x, char *buf);
  * capped by what is resident; 255 restores automatic), threads per block (128 / 256 / 512, default 256) and the
  * number of waiting lanes at which a warp resolves / refills (default 4).  0 keeps the current value. */
 int mc3d_set_launch(mc3d_ctx *ctx, int blocks_per_sm, int block_threads, int refill_threshold);
+
+/* Which kernels walk the photons.  MC3D_PATH_PERSISTENT: init -> persistent-warp walk -> finalize, per-photon state
+ * handed through HBM (made for walks of tens to millions of events).  MC3D_PATH_FUSED: one kernel, one thread per
+ * photon from its first draw to its record (made for walks of a few events: strongly absorbing grains, thin slabs,
+ * Lambertian_surface).  MC3D_PATH_AUTO (default) picks from the table's single-scattering albedo and tau_tot.  A
+ * performance choice only: both follow the same per-photon random stream and return bit-identical results. */
+#define MC3D_PATH_AUTO 0
+#define MC3D_PATH_FUSED 1
+#define MC3D_PATH_PERSISTENT 2
+int mc3d_set_walk_path(mc3d_ctx *ctx, int path);
 
 /* Input caching (default on): a call whose SSP table, bin edges and histogram edges equal what its slot uploaded
  * last time skips the host-to-device copy (a few KB).  enabled = 0 makes every call upload its inputs again. */

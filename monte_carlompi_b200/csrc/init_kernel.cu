@@ -18,13 +18,13 @@
 
 namespace mc3d {
 
-template <bool IMP, int BLOCK>
+template <bool IMP, bool SWEEP, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) init_kernel(const __grid_constant__ WalkParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     DevRow *rows = reinterpret_cast<DevRow *>(smem_raw);
-    for (int k = threadIdx.x; k < P.n_rows * (int)(sizeof(DevRow) / 4); k += BLOCK)
-        reinterpret_cast<uint32_t *>(rows)[k] = reinterpret_cast<const uint32_t *>(P.rows)[k];
+    const DevCase *cases = staged_cases(P, smem_raw);
+    stage_tables(P, smem_raw, BLOCK);
     __syncthreads();
     const uint32_t rows_addr = shared_address(rows);
     const uint32_t lane = threadIdx.x & 31u;
@@ -32,21 +32,22 @@ __global__ void __launch_bounds__(BLOCK) init_kernel(const __grid_constant__ Wal
     for (uint32_t base = (blockIdx.x * BLOCK + (threadIdx.x & ~31u)); base < P.n_photon; base += gridDim.x * BLOCK) {
         const uint32_t pid = base + lane;
         bool survive = false;
+        uint32_t redo = 0u;
         float dtau = 0.0f;
-        uint32_t row = 0;
+        uint32_t row = 0, lcase = 0;
         if (pid < P.n_photon) {
             Lane L;
-            uint32_t cond = first_event<IMP>(P, rows, rows_addr, (uint32_t)P.photon_begin + pid, L, row, dtau);
-            if (cond == ALIVE && L.i != 1u) {
-                // reflected off the Lambertian bottom on its first step and still alive after event 2: it no
-                // longer has the "fresh photon" state, so it is walked to completion here (thin slabs only; those
-                // normally take the fused kernel anyway)
-                do {
-                    if (!group<IMP, true>(P, rows, rows_addr, L)) cond = resolve<IMP>(P, rows[row], L);
-                } while (cond == ALIVE);
-            }
+            lcase = find_case<SWEEP>(P, cases, pid);
+            const DevCase &C = SWEEP ? cases[lcase] : P.c;
+            const uint64_t id = C.id0 + pid;
+            uint32_t cond = first_event<IMP>(P, C, (uint32_t)(id >> 32), rows, rows_addr, (uint32_t)id, L, row, dtau, redo);
+            // Event 1 needed attention and the photon is still alive (reflected off a Lambertian bottom on its first
+            // step, possibly through event 2 already; or a weakly absorbing row whose coarse key asked for the fine
+            // test / a renormalisation): it is handed over in its state after the MOVE of event 1, with the event's
+            // key and species in Fresh::redo, and the walk kernel's resolve pass redoes the chain of event 1
+            // (deterministic: same blocks, same result)
             if (cond == ALIVE) survive = true;
-            else store_raw(P, pid, L.ux, L.uy, L.uz, L.path_hi + L.path_lo, L.i - 1u, cond, row);
+            else store_raw(P, pid, L.ux, L.uy, L.uz, __fadd_rn(L.path_hi, L.path_lo), L.i - 1u, cond, row, lcase);
         }
         const uint32_t m = __ballot_sync(0xffffffffu, survive);
         uint32_t slot0 = 0;
@@ -54,26 +55,32 @@ __global__ void __launch_bounds__(BLOCK) init_kernel(const __grid_constant__ Wal
         slot0 = __shfl_sync(0xffffffffu, slot0, 0);
         if (survive) {
             Fresh f;
-            f.pid = pid; f.row = row; f.dtau = dtau; f.pad = 0u;
+            f.pid = pid; f.row = row | (lcase << 12); f.dtau = dtau; f.redo = redo;
             *reinterpret_cast<uint4 *>(P.fresh + slot0 + __popc(m & ((1u << lane) - 1u))) = *reinterpret_cast<uint4 *>(&f);
         }
     }
 }
 
-cudaError_t launch_init(const WalkParams &P, bool impurity, int sm_count, cudaStream_t stream)
+template <bool IMP, bool SWEEP>
+static cudaError_t launch_init_variant(const WalkParams &P, int sm_count, cudaStream_t stream)
 {
     constexpr int BLOCK = 256;
-    const size_t smem = (size_t)P.n_rows * sizeof(DevRow);
+    const size_t smem = tables_bytes(P.n_rows, P.n_cases);
     const long long want = ((long long)P.n_photon + BLOCK - 1) / BLOCK;
     const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)sm_count * 8));
-    if (impurity) {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(init_kernel<true, BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        init_kernel<true, BLOCK><<<grid, BLOCK, smem, stream>>>(P);
-    } else {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(init_kernel<false, BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        init_kernel<false, BLOCK><<<grid, BLOCK, smem, stream>>>(P);
+    auto kern = init_kernel<IMP, SWEEP, BLOCK>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
     }
+    kern<<<grid, BLOCK, smem, stream>>>(P);
     return cudaGetLastError();
+}
+
+cudaError_t launch_init(const WalkParams &P, bool impurity, int sm_count, cudaStream_t stream)
+{
+    if (P.n_cases) return impurity ? launch_init_variant<true, true>(P, sm_count, stream) : launch_init_variant<false, true>(P, sm_count, stream);
+    return impurity ? launch_init_variant<true, false>(P, sm_count, stream) : launch_init_variant<false, false>(P, sm_count, stream);
 }
 
 }  // namespace mc3d

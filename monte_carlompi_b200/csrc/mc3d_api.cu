@@ -33,6 +33,7 @@ cudaError_t launch_walk(const WalkParams &P, bool impurity, int block_threads, i
                         cudaStream_t stream, int *occupancy);
 cudaError_t launch_init(const WalkParams &P, bool impurity, int sm_count, cudaStream_t stream);
 cudaError_t launch_finalize(const FinalizeParams &P, int sm_count, cudaStream_t stream);
+cudaError_t launch_fused(const WalkParams &P, const FinalizeParams &F, bool impurity, int sm_count, cudaStream_t stream);
 cudaError_t launch_replay(const ReplayParams &P, cudaStream_t stream);
 }  // namespace mc3d
 
@@ -145,7 +146,7 @@ struct Slot {
     // tally[tally_len] | n_events | extrema (2 words) + column histograms | claim counters (2 x uint32 per chunk)
     DevBuf<unsigned long long> acc;
     unsigned long long *host_acc = nullptr; // pinned mirror of tally .. column histograms
-    size_t host_acc_cap = 0, extras_len = 0;
+    size_t host_acc_cap = 0, extras_len = 0, n_case_ev = 0;
     DevBuf<Fresh> fresh;                    // photons that survived their first event (init kernel -> walk kernel)
     DevBuf<RawResult> raw;
     DevBuf<uint8_t> recs;                   // record columns of one chunk, packed like mc3d_records_layout
@@ -157,6 +158,7 @@ struct Slot {
     size_t tally_len = 0;
     int n_chunks = 0;
     uint64_t *user_tally = nullptr;
+    uint64_t *user_case_ev = nullptr;       // sweeps: events per case
     bool packed = false;                    // the pending call returns packed records
 };
 
@@ -174,10 +176,13 @@ struct mc3d_ctx {
     int rank = 0, world = 1;
     int blocks_per_sm = 0;   // 0 = automatic: enough lanes for >= 26 photons each, at most the resident capacity
     int block_threads = 256, refill_threshold = 4;
-    struct Occupancy { bool impurity; int block_threads, bps_variant, n_rows, resident; };
+    struct Occupancy { bool impurity; int block_threads, bps_variant, n_rows; uint32_t n_cases; int resident; };
     std::vector<Occupancy> occupancy;   // resident walk-kernel blocks per SM, queried once per variant
     bool input_caching = true; // skip the upload of inputs identical to the slot's previous call
     int drain_give = -1;       // -1 = automatic (16 when other calls are in flight, else off); MC3D_DRAIN_GIVE overrides
+    int drain_latency = -1;    // -1 = automatic (on for a call that runs alone); MC3D_DRAIN_LATENCY overrides
+    int walk_path = MC3D_PATH_AUTO;   // mc3d_set_walk_path / MC3D_WALK_PATH
+    double fused_max_events = 12.0;   // automatic path: fused kernel when a photon is expected to end within this many events
     std::chrono::steady_clock::time_point t0[N_SLOTS];
     mc3d_stats pending_stats[N_SLOTS];
     bool hist_on = false;
@@ -211,7 +216,7 @@ static void threshold40(double ssa, uint32_t *t16, uint32_t *t24)
     *t24 = (uint32_t)(T & 0xffffffu);
 }
 
-static bool build_rows(const mc3d_params *P, const mc3d_ssp_row *table, int n_rows, DevRow *out)
+static bool build_rows(const mc3d_params *P, const mc3d_ssp_row *table, int n_rows, float neg_tau_tot, DevRow *out)
 {
     bool impurity = false;
     for (int r = 0; r < n_rows; ++r) {
@@ -227,7 +232,7 @@ static bool build_rows(const mc3d_params *P, const mc3d_ssp_row *table, int n_ro
         threshold40(s.ssa_imp, &d.ti16, &d.ti24);
         d.t_hot = std::min(d.t16, RENORM_KEY) << 16;
         d.ti_hot = std::min(d.ti16, RENORM_KEY) << 16;
-        d.pad = 0u;
+        d.neg_tau_tot = neg_tau_tot;
         // impurity iff (w + 1/2) 2^-32 <= P_ext_imp  <=>  w <= floor(P 2^32 - 1/2)
         const double sl = std::floor(std::ldexp(s.p_ext_imp, 32) - 0.5);
         if (sl >= 0.0) {
@@ -241,6 +246,21 @@ static bool build_rows(const mc3d_params *P, const mc3d_ssp_row *table, int n_ro
         d.inv_ext = (float)(0.6931471805599453 / (s.ext_cff_mss * P->rho_snw));
     }
     return impurity;
+}
+
+// Rough number of events a photon of the centre wavelength lives (only used to pick the kernel: a performance
+// choice, the results do not depend on it).  It ends by absorption after ~1 / (1 - ssa) events, or by leaving a slab
+// of optical depth tau through a face after ~(1 + tau)(1 + tau (1 - g)) events (a reflecting bottom sends it back).
+static double expected_events(const mc3d_params *P, const mc3d_ssp_row *table, int n_rows)
+{
+    if (P->flags & MC3D_FLAG_LAMBERT_SURFACE) return 2.0;
+    const int r = std::max(0, std::min(n_rows - 1, (int)std::lrint(P->wvl0_um * 100.0) - P->k_first));
+    const mc3d_ssp_row &s = table[r];
+    const double a = (1.0 - s.p_ext_imp) * (1.0 - s.ssa_ice) + s.p_ext_imp * (1.0 - s.ssa_imp);
+    const double by_absorption = 1.0 / std::max(a, 1e-12);
+    double by_escape = (1.0 + P->tau_tot) * (1.0 + P->tau_tot * (1.0 - s.g));
+    if (P->flags & MC3D_FLAG_LAMBERT_BOTTOM) by_escape *= 1.0 + 2.0 * std::max(0.0, std::min(1.0, P->r_lambert));
+    return std::min(by_absorption, by_escape);
 }
 
 // np.linspace(start, stop, n + 1): arange * step + start with the endpoint forced (numpy/_core/function_base.py)
@@ -329,6 +349,13 @@ static void apply_env(mc3d_ctx *ctx)
 {
     const char *e = getenv("MC3D_DRAIN_GIVE");        // experiments only; results do not depend on it
     if (e && *e) ctx->drain_give = std::max(0, std::min(31, atoi(e)));
+    e = getenv("MC3D_DRAIN_LATENCY");
+    if (e && *e) ctx->drain_latency = atoi(e) ? 1 : 0;
+    e = getenv("MC3D_WALK_PATH");                     // same: "fused" | "persistent" | "auto"
+    if (e && !strcmp(e, "fused")) ctx->walk_path = MC3D_PATH_FUSED;
+    if (e && !strcmp(e, "persistent")) ctx->walk_path = MC3D_PATH_PERSISTENT;
+    e = getenv("MC3D_FUSED_MAX_EVENTS");
+    if (e && *e) ctx->fused_max_events = atof(e);
 }
 
 int mc3d_create(mc3d_ctx **out, const int *device_ids, int n_dev)
@@ -479,6 +506,16 @@ int mc3d_set_launch(mc3d_ctx *ctx, int blocks_per_sm, int block_threads, int ref
     return MC3D_OK;
 }
 
+int mc3d_set_walk_path(mc3d_ctx *ctx, int path)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (path != MC3D_PATH_AUTO && path != MC3D_PATH_FUSED && path != MC3D_PATH_PERSISTENT)
+        return fail(MC3D_EINVAL, "path must be MC3D_PATH_AUTO, MC3D_PATH_FUSED or MC3D_PATH_PERSISTENT");
+    ctx->walk_path = path;
+    return MC3D_OK;
+}
+
 static int validate_run(const mc3d_params *P, const mc3d_ssp_row *table, int n_rows)
 {
     if (!P || !table) return fail(MC3D_EINVAL, "params / table is null");
@@ -499,22 +536,58 @@ static int validate_run(const mc3d_params *P, const mc3d_ssp_row *table, int n_r
     return MC3D_OK;
 }
 
-static int run_async_impl(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, const mc3d_ssp_row *table, int n_rows,
-                          uint64_t seed, uint64_t photon_begin, uint64_t n_photon, const mc3d_records *rec, uint64_t *tally);
+// One call: one case (mc3d_run / mc3d_run_async) or a sweep of cases walked by the same launches (mc3d_run_sweep*).
+namespace {
+struct HostCase {
+    mc3d_params params;
+    int row_begin, n_rows;   // the case's rows in the call's table
+    uint64_t id_begin;       // global photon id of the case's first photon
+    uint64_t first;          // its position in the call's concatenated photon space
+    uint64_t n_photon;
+};
+struct Job {
+    std::vector<HostCase> cases;
+    bool sweep = false;
+    const mc3d_ssp_row *table = nullptr;
+    int n_rows = 0;                       // rows of the whole table
+    uint64_t seed = 0;
+    uint64_t range_begin = 0, range_count = 0;   // the part of the concatenated photon space this context walks
+    const mc3d_records *rec = nullptr;    // indexed from range_begin
+    uint64_t *tally = nullptr;
+    uint64_t *case_events = nullptr;      // [cases.size()] or null (sweeps)
+    int n_theta_bins = 0, n_phi_bins = 0;
+};
 
-int mc3d_run_async(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, const mc3d_ssp_row *table, int n_rows,
-                   uint64_t seed, uint64_t photon_begin, uint64_t n_photon, const mc3d_records *rec,
-                   uint64_t *tally, mc3d_stats *stats)
+DevCase make_devcase(const mc3d_params *P, int row_begin, int n_rows)
 {
-    if (stats) memset(stats, 0, sizeof *stats);   // filled by mc3d_wait (the call has not run yet)
-    int rc = check_ctx(ctx);
-    if (rc) return rc;
-    if (slot_idx < 0 || slot_idx >= N_SLOTS) return fail(MC3D_EINVAL, "slot must be in [0, %d)", N_SLOTS);
-    rc = validate_run(P, table, n_rows);
-    if (rc) return rc;
+    DevCase c;
+    memset(&c, 0, sizeof c);
+    c.row_begin = (uint32_t)row_begin;
+    c.n_rows = n_rows;
+    c.mu0x = (float)std::sin(P->theta0_rad);
+    if (c.mu0x == 0.0f) c.mu0x = -1e-12f;   // vertical incidence: see apply_event (reproduces the muz_0 == -1 branch)
+    c.mu0z = (float)(-std::cos(P->theta0_rad));
+    c.tau_tot = (float)(P->tau_tot / 0.6931471805599453);   // the walk's depth unit is ln 2 optical depths
+    c.neg_tau_tot = -c.tau_tot;
+    c.wvl0_x100 = P->wvl0_um * 100.0;
+    c.sigma_x100 = P->sigma_um * 100.0;
+    c.k_first = P->k_first;
+    const double t = std::floor(std::ldexp(P->r_lambert, 32) - 0.5);
+    c.refl_thr = t < -1.0 ? -1 : (t > 4294967295.0 ? 4294967295ll : (long long)t);
+    c.lambert_bottom = (P->flags & MC3D_FLAG_LAMBERT_BOTTOM) ? 1u : 0u;
+    c.lambert_surface = (P->flags & MC3D_FLAG_LAMBERT_SURFACE) ? 1u : 0u;
+    threshold40(P->r_lambert, &c.surf_t16, &c.surf_t24);
+    return c;
+}
+}  // namespace
+
+static int run_job(mc3d_ctx *ctx, int slot_idx, const Job &J);
+
+static int start_job(mc3d_ctx *ctx, int slot_idx, const Job &J)
+{
     for (Device &d : ctx->devs)
         if (d.slot[slot_idx].busy) return fail(MC3D_EINVAL, "slot %d is busy; call mc3d_wait first", slot_idx);
-    rc = run_async_impl(ctx, slot_idx, P, table, n_rows, seed, photon_begin, n_photon, rec, tally);
+    int rc = run_job(ctx, slot_idx, J);
     if (rc) {
         // a failure half way (allocation, launch, NCCL): drain whatever was enqueued and give the slot back, so the
         // context stays usable and no copy into the caller's buffers is left in flight; the error text is kept
@@ -527,43 +600,110 @@ int mc3d_run_async(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, const mc3d
     return rc;
 }
 
-static int run_async_impl(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, const mc3d_ssp_row *table, int n_rows,
-                          uint64_t seed, uint64_t photon_begin, uint64_t n_photon, const mc3d_records *rec, uint64_t *tally)
+int mc3d_run_async(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, const mc3d_ssp_row *table, int n_rows,
+                   uint64_t seed, uint64_t photon_begin, uint64_t n_photon, const mc3d_records *rec,
+                   uint64_t *tally, mc3d_stats *stats)
+{
+    if (stats) memset(stats, 0, sizeof *stats);   // filled by mc3d_wait (the call has not run yet)
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (slot_idx < 0 || slot_idx >= N_SLOTS) return fail(MC3D_EINVAL, "slot must be in [0, %d)", N_SLOTS);
+    rc = validate_run(P, table, n_rows);
+    if (rc) return rc;
+    Job J;
+    J.cases.push_back(HostCase{*P, 0, n_rows, photon_begin, 0, n_photon});
+    J.table = table; J.n_rows = n_rows; J.seed = seed;
+    J.range_begin = 0; J.range_count = n_photon;
+    J.rec = rec; J.tally = tally;
+    J.n_theta_bins = P->n_theta_bins; J.n_phi_bins = P->n_phi_bins;
+    return start_job(ctx, slot_idx, J);
+}
+
+int mc3d_run_sweep_async(mc3d_ctx *ctx, int slot_idx, const mc3d_sweep_case *cases, int n_cases, const mc3d_ssp_row *table,
+                         int n_rows_total, uint64_t seed, uint64_t range_begin, uint64_t range_count,
+                         const mc3d_records *rec, uint64_t *tally, uint64_t *case_events)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (slot_idx < 0 || slot_idx >= N_SLOTS) return fail(MC3D_EINVAL, "slot must be in [0, %d)", N_SLOTS);
+    if (!cases || n_cases < 1 || n_cases > MC3D_SWEEP_MAX_CASES)
+        return fail(MC3D_EINVAL, "n_cases must be in [1, %d]", MC3D_SWEEP_MAX_CASES);
+    if (!table || n_rows_total < 1 || n_rows_total > 2048)
+        return fail(MC3D_EINVAL, "n_rows_total %d out of range [1, 2048] (rows are staged in shared memory)", n_rows_total);
+    Job J;
+    J.sweep = true;
+    J.table = table; J.n_rows = n_rows_total; J.seed = seed;
+    J.rec = rec; J.tally = tally; J.case_events = case_events;
+    J.n_theta_bins = cases[0].params.n_theta_bins; J.n_phi_bins = cases[0].params.n_phi_bins;
+    uint64_t total = 0;
+    for (int c = 0; c < n_cases; ++c) {
+        const mc3d_sweep_case &s = cases[c];
+        if (s.row_begin < 0 || s.n_rows < 1 || (int64_t)s.row_begin + s.n_rows > n_rows_total)
+            return fail(MC3D_EINVAL, "case %d: rows [%d, %d) outside the table of %d rows", c, s.row_begin, s.row_begin + s.n_rows, n_rows_total);
+        rc = validate_run(&s.params, table + s.row_begin, s.n_rows);
+        if (rc) return rc;
+        if (s.params.n_theta_bins != J.n_theta_bins || s.params.n_phi_bins != J.n_phi_bins)
+            return fail(MC3D_EINVAL, "case %d: all cases of a sweep share n_theta_bins / n_phi_bins", c);
+        if (s.n_photon >= (1ull << 40)) return fail(MC3D_EINVAL, "case %d: n_photon must be < 2^40", c);
+        // a row carries its case's slab depth and density: cases may share rows only if those agree
+        for (int o = 0; o < c; ++o) {
+            const mc3d_sweep_case &t = cases[o];
+            const bool disjoint = t.row_begin + t.n_rows <= s.row_begin || s.row_begin + s.n_rows <= t.row_begin;
+            const bool same = t.row_begin == s.row_begin && t.n_rows == s.n_rows;
+            if (!disjoint && !(same && t.params.tau_tot == s.params.tau_tot && t.params.rho_snw == s.params.rho_snw))
+                return fail(MC3D_EINVAL, "cases %d and %d: cases share rows only as identical ranges with equal tau_tot and rho_snw", o, c);
+        }
+        J.cases.push_back(HostCase{s.params, s.row_begin, s.n_rows, (uint64_t)c << 40, total, s.n_photon});
+        total += s.n_photon;
+    }
+    if (range_begin > total || range_count > total - range_begin)
+        return fail(MC3D_EINVAL, "photon range [%llu, +%llu) outside the sweep's %llu photons", (unsigned long long)range_begin,
+                    (unsigned long long)range_count, (unsigned long long)total);
+    J.range_begin = range_begin; J.range_count = range_count;
+    return start_job(ctx, slot_idx, J);
+}
+
+int mc3d_run_sweep(mc3d_ctx *ctx, const mc3d_sweep_case *cases, int n_cases, const mc3d_ssp_row *table, int n_rows_total,
+                   uint64_t seed, const mc3d_records *rec, uint64_t *tally, uint64_t *case_events, mc3d_stats *stats)
+{
+    if (stats) memset(stats, 0, sizeof *stats);
+    uint64_t total = 0;
+    for (int c = 0; cases && c < n_cases; ++c) total += cases[c].n_photon;
+    int rc = mc3d_run_sweep_async(ctx, 0, cases, n_cases, table, n_rows_total, seed, 0, total, rec, tally, case_events);
+    if (rc) return rc;
+    return mc3d_wait(ctx, 0, stats);
+}
+
+static int run_job(mc3d_ctx *ctx, int slot_idx, const Job &J)
 {
     ctx->t0[slot_idx] = std::chrono::steady_clock::now();
 
     const int n_dev = (int)ctx->devs.size();
-    const int n_phi = std::max(1, P->n_phi_bins);
-    const size_t stride = N_COND + (size_t)P->n_theta_bins * n_phi;
+    const int n_rows = J.n_rows;
+    const int n_phi = std::max(1, J.n_phi_bins);
+    const size_t stride = N_COND + (size_t)J.n_theta_bins * n_phi;
     const size_t tally_len = (size_t)n_rows * stride;
-    const size_t n_edges = (size_t)P->n_theta_bins + 1 + (size_t)n_phi + 1;
+    const size_t n_edges = (size_t)J.n_theta_bins + 1 + (size_t)n_phi + 1;
+    const size_t n_case_ev = (J.sweep && J.case_events) ? J.cases.size() : 0;
 
     WalkParams W;
     memset(&W, 0, sizeof W);
-    philox_round_keys(seed, W.rk);
-    W.mu0x = (float)std::sin(P->theta0_rad);
-    if (W.mu0x == 0.0f) W.mu0x = -1e-12f;   // vertical incidence: see scatter_and_move (reproduces the muz_0 == -1 branch)
-    W.mu0z = (float)(-std::cos(P->theta0_rad));
-    W.tau_tot = (float)(P->tau_tot / 0.6931471805599453);   // the walk's depth unit is ln 2 optical depths
-    W.neg_tau_tot = -W.tau_tot;
-    W.wvl0_x100 = P->wvl0_um * 100.0;
-    W.sigma_x100 = P->sigma_um * 100.0;
-    W.k_first = P->k_first;
+    philox_round_keys(J.seed, W.rk);
     W.n_rows = n_rows;
-    {
-        const double t = std::floor(std::ldexp(P->r_lambert, 32) - 0.5);
-        W.refl_thr = t < -1.0 ? -1 : (t > 4294967295.0 ? 4294967295ll : (long long)t);
-    }
-    W.lambert_bottom = (P->flags & MC3D_FLAG_LAMBERT_BOTTOM) ? 1u : 0u;
-    W.lambert_surface = (P->flags & MC3D_FLAG_LAMBERT_SURFACE) ? 1u : 0u;
-    threshold40(P->r_lambert, &W.surf_t16, &W.surf_t24);
     W.refill_threshold = (uint32_t)ctx->refill_threshold;
+    bool lone = true;
     {   // drain-phase consolidation pays when other launches can use the issue slots it frees, i.e. when other
-        // calls are in flight on this context; a call running alone would only see its tail get longer
+        // calls are in flight on this context; a call running alone is bound by the dependent chain of its longest
+        // walks instead and takes the latency-oriented drain loop
         bool others_busy = false;
         for (int s = 0; s < N_SLOTS; ++s) others_busy |= (s != slot_idx && ctx->devs[0].slot[s].busy);
         W.drain_give = ctx->drain_give >= 0 ? (uint32_t)ctx->drain_give : (others_busy ? 16u : 0u);
+        W.drain_latency = ctx->drain_latency >= 0 ? (uint32_t)ctx->drain_latency : (others_busy ? 0u : 1u);
+        lone = !others_busy;
     }
+    double longest = 0.0;   // expected events per photon of the longest-lived case
+    for (const HostCase &c : J.cases) longest = std::max(longest, expected_events(&c.params, J.table + c.row_begin, c.n_rows));
+    const bool fused = ctx->walk_path == MC3D_PATH_FUSED || (ctx->walk_path == MC3D_PATH_AUTO && longest <= ctx->fused_max_events);
 
     ctx->done_hist[slot_idx] = ctx->hist_on;
     ctx->done_spec[slot_idx] = ctx->hist_spec;
@@ -574,26 +714,42 @@ static int run_async_impl(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, con
     st.sm_count = ctx->devs[0].sm_count;
     st.sm_clock_khz = ctx->devs[0].clock_khz;
     st.block_threads = ctx->block_threads;
-    st.n_photon = n_photon;
+    st.n_photon = J.range_count;
+    st.walk_path = fused ? MC3D_PATH_FUSED : MC3D_PATH_PERSISTENT;
 
     for (int k = 0; k < n_dev; ++k) {
         Device &d = ctx->devs[k];
         Slot &s = d.slot[slot_idx];
         uint64_t off, cnt;
-        array_split(n_photon, n_dev, k, &off, &cnt);
+        array_split(J.range_count, n_dev, k, &off, &cnt);   // this device's part of the range, relative to range_begin
         CUDA_TRY(cudaSetDevice(d.id));
-        // chunks of <= 2^26 photons that never cross a multiple of 2^32 in the global photon id (the walk kernel
-        // carries only the low id word per lane; the high word is a launch constant)
+        // Chunks of <= 2^26 photons.  A single-case launch never crosses a multiple of 2^32 in the global photon id
+        // (its lanes carry only the low id word; the high word is a launch constant); sweep lanes carry both words.
         std::vector<std::pair<uint64_t, uint32_t>> chunks;   // (offset in this device's range, count)
         for (uint64_t c_off = 0; c_off < cnt;) {
-            const uint64_t gid = photon_begin + off + c_off;
-            const uint64_t to_wrap = 0x100000000ull - (gid & 0xffffffffull);
-            const uint64_t c = std::min<uint64_t>(std::min<uint64_t>(CHUNK_PHOTONS, cnt - c_off), to_wrap);
+            uint64_t c = std::min<uint64_t>(CHUNK_PHOTONS, cnt - c_off);
+            if (!J.sweep) {
+                const uint64_t gid = J.cases[0].id_begin + J.range_begin + off + c_off;
+                c = std::min<uint64_t>(c, 0x100000000ull - (gid & 0xffffffffull));
+            }
             chunks.emplace_back(c_off, (uint32_t)c);
             c_off += c;
         }
         const int n_chunks = (int)chunks.size();
         const uint64_t chunk_cap = std::min<uint64_t>(cnt, CHUNK_PHOTONS);
+        // sweep: the cases overlapping each chunk, as consecutive case indices [lo, hi]
+        std::vector<std::pair<int, int>> chunk_cases(n_chunks, std::make_pair(0, 0));
+        size_t n_case_entries = 0;
+        if (J.sweep) {
+            for (int c = 0; c < n_chunks; ++c) {
+                const uint64_t g0 = J.range_begin + off + chunks[c].first, g1 = g0 + chunks[c].second;   // [g0, g1)
+                int lo = 0, hi = (int)J.cases.size() - 1;
+                while (lo < hi && J.cases[lo].first + J.cases[lo].n_photon <= g0) ++lo;
+                while (hi > lo && J.cases[hi].first >= g1) --hi;
+                chunk_cases[c] = std::make_pair(lo, hi);
+                n_case_entries += (size_t)(hi - lo + 1);
+            }
+        }
 
         // ---- buffers
         const bool hist_on = ctx->hist_on;
@@ -601,15 +757,19 @@ static int run_async_impl(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, con
         const size_t n_hist = hist_on ? (size_t)hs.n_scat_bins + (size_t)hs.path_bins : 0;
         const size_t n_hist_edges = hist_on ? n_hist + 2 : 0;
         const size_t rows_bytes = (size_t)n_rows * sizeof(DevRow);
-        const size_t cst_bytes = rows_bytes + (n_edges + n_hist_edges) * sizeof(double);
+        const size_t edges_bytes = (n_edges + n_hist_edges) * sizeof(double);
+        const size_t cst_bytes = rows_bytes + edges_bytes + n_case_entries * sizeof(DevCase);
         s.extras_len = 2 + n_hist;
-        const size_t acc_copy = tally_len + 1 + s.extras_len;                     // words copied back
+        s.n_case_ev = n_case_ev;
+        const size_t acc_copy = tally_len + 1 + s.extras_len + n_case_ev;          // words copied back
         const size_t acc_words = acc_copy + (size_t)std::max(n_chunks, 1);        // + one word (2 counters) per chunk
         const bool cst_moved = s.cst.cap < cst_bytes;
         CUDA_TRY(s.cst.ensure(cst_bytes));
         CUDA_TRY(s.acc.ensure(acc_words));
-        CUDA_TRY(s.fresh.ensure(std::max<uint64_t>(chunk_cap, 1)));
-        CUDA_TRY(s.raw.ensure(std::max<uint64_t>(chunk_cap, 1)));
+        if (!fused) {   // the fused kernel keeps a photon in registers from its first draw to its record
+            CUDA_TRY(s.fresh.ensure(std::max<uint64_t>(chunk_cap, 1)));
+            CUDA_TRY(s.raw.ensure(std::max<uint64_t>(chunk_cap, 1)));
+        }
         if (s.host_cst_cap < cst_bytes) {
             if (s.host_cst) cudaFreeHost(s.host_cst);
             s.host_cst = nullptr;
@@ -622,9 +782,12 @@ static int run_async_impl(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, con
             CUDA_TRY(cudaHostAlloc((void **)&s.host_acc, acc_copy * sizeof(unsigned long long), cudaHostAllocPortable));
             s.host_acc_cap = acc_copy;
         }
+        const mc3d_records *rec = J.rec;
         const bool want_packed = rec != nullptr && rec->packed != nullptr && cnt != 0;
-        if (want_packed && n_rows > MC3D_PACKED_MAX_ROWS)
-            return fail(MC3D_EINVAL, "packed records support tables of <= %d rows (got %d): use the record columns", MC3D_PACKED_MAX_ROWS, n_rows);
+        if (want_packed)
+            for (const HostCase &c : J.cases)
+                if (c.n_rows > MC3D_PACKED_MAX_ROWS)
+                    return fail(MC3D_EINVAL, "packed records support tables of <= %d rows per case (got %d): use the record columns", MC3D_PACKED_MAX_ROWS, c.n_rows);
         const bool want_rec = rec != nullptr && cnt != 0 && !want_packed;
         void *const host_col[6] = {rec ? (void *)rec->condition : nullptr, rec ? (void *)rec->wvl_row : nullptr,
                                    rec ? (void *)rec->theta_n : nullptr,   rec ? (void *)rec->phi_n : nullptr,
@@ -647,16 +810,24 @@ static int run_async_impl(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, con
         DevRow *d_rows = reinterpret_cast<DevRow *>(s.cst.p);
         double *d_edges = reinterpret_cast<double *>(s.cst.p + rows_bytes);
         double *d_hist_edges = d_edges + n_edges;
+        DevCase *d_cases = reinterpret_cast<DevCase *>(s.cst.p + rows_bytes + edges_bytes);
         unsigned long long *d_tally = s.acc.p, *d_extras = s.acc.p + tally_len + 1;
+        unsigned long long *d_case_ev = n_case_ev ? d_extras + s.extras_len : nullptr;
         uint32_t *d_counters = reinterpret_cast<uint32_t *>(s.acc.p + acc_copy);
 
         // ---- inputs: staged in pinned memory, uploaded only when they differ from what the slot's block holds
         DevRow *h_rows = reinterpret_cast<DevRow *>(s.host_cst);
         double *h_edges = reinterpret_cast<double *>(s.host_cst + rows_bytes);
-        const bool impurity = build_rows(P, table, n_rows, h_rows);
-        if (P->n_theta_bins > 0) linspace_edges(0.0, 1.5707963267948966, P->n_theta_bins, h_edges);   // np.linspace(0, pi/2, n + 1)
+        DevCase *h_cases = reinterpret_cast<DevCase *>(s.host_cst + rows_bytes + edges_bytes);
+        memset(h_rows, 0, rows_bytes);   // rows no case uses stay zero
+        bool impurity = false;
+        for (const HostCase &c : J.cases) {
+            const float neg_tau = make_devcase(&c.params, c.row_begin, c.n_rows).neg_tau_tot;
+            impurity |= build_rows(&c.params, J.table + c.row_begin, c.n_rows, neg_tau, h_rows + c.row_begin);
+        }
+        if (J.n_theta_bins > 0) linspace_edges(0.0, 1.5707963267948966, J.n_theta_bins, h_edges);   // np.linspace(0, pi/2, n + 1)
         else h_edges[0] = 0.0;
-        linspace_edges(0.0, 6.283185307179586, n_phi, h_edges + P->n_theta_bins + 1);               // np.linspace(0, 2 pi, m + 1)
+        linspace_edges(0.0, 6.283185307179586, n_phi, h_edges + J.n_theta_bins + 1);               // np.linspace(0, 2 pi, m + 1)
         if (hist_on) {
             double *h_hist = h_edges + n_edges;
             if (hs.n_scat_bins > 0) linspace_edges(hs.n_scat_lo, hs.n_scat_hi, hs.n_scat_bins, h_hist);
@@ -664,45 +835,74 @@ static int run_async_impl(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, con
             if (hs.path_bins > 0) linspace_edges(hs.path_lo, hs.path_hi, hs.path_bins, h_hist + hs.n_scat_bins + 1);
             else h_hist[hs.n_scat_bins + 1] = 0.0;
         }
+        {   // sweep: per chunk, the cases it overlaps with their position in the chunk
+            size_t at = 0;
+            for (int c = 0; J.sweep && c < n_chunks; ++c) {
+                const uint64_t g0 = J.range_begin + off + chunks[c].first;
+                for (int q = chunk_cases[c].first; q <= chunk_cases[c].second; ++q) {
+                    const HostCase &hc = J.cases[q];
+                    DevCase dc = make_devcase(&hc.params, hc.row_begin, hc.n_rows);
+                    dc.id0 = hc.id_begin - hc.first + g0;                       // id = id0 + pid (modulo 2^64)
+                    dc.pid_first = (uint32_t)(std::max(hc.first, g0) - g0);      // < 2^26
+                    h_cases[at++] = dc;
+                }
+            }
+        }
         if (!ctx->input_caching || cst_moved || s.cst_shadow.size() != cst_bytes || memcmp(s.cst_shadow.data(), s.host_cst, cst_bytes) != 0) {
             CUDA_TRY(cudaMemcpyAsync(s.cst.p, s.host_cst, cst_bytes, cudaMemcpyHostToDevice, s.stream));
             s.cst_shadow.assign(s.host_cst, s.host_cst + cst_bytes);
         }
         // tallies, event count, extrema (the minima are kept complemented, so everything starts at 0), column
-        // histograms and the claim counters
+        // histograms, events per case and the claim counters
         CUDA_TRY(cudaMemsetAsync(s.acc.p, 0, acc_words * sizeof(unsigned long long), s.stream));
 
         // ---- launch configuration: persistent grid, SM count x resident blocks
-        // Persistent grid.  A launch ends with a drain phase in which lanes that found no more photons idle while
-        // the longest walks finish; its cost grows with the number of lanes, so a launch gets only as many lanes
-        // as keep >= 26 photons per lane (at most the resident capacity, at least one block per SM).  Small
-        // launches then leave room for the next calls in flight on the other slots' streams.
+        // A launch ends with a drain phase in which lanes that found no more photons idle while the longest walks
+        // finish; its cost grows with the number of lanes, so a launch gets only as many lanes as keep >= 26 photons
+        // per lane (13 for a call that runs alone: its ramp-down is bound by latency, not by issue slots; at most the
+        // resident capacity, at least one block per SM).  Small launches then leave room for the next calls in flight
+        // on the other slots' streams.
         const int bps_variant = ctx->blocks_per_sm > 0 ? ctx->blocks_per_sm : 1024 / ctx->block_threads;
+        const uint32_t max_chunk_cases = [&] { int m = 0; for (auto &cc : chunk_cases) m = std::max(m, cc.second - cc.first + 1); return (uint32_t)(J.sweep ? m : 0); }();
         int resident = 0;
         for (const mc3d_ctx::Occupancy &o : ctx->occupancy)
-            if (o.impurity == impurity && o.block_threads == ctx->block_threads && o.bps_variant == bps_variant && o.n_rows == n_rows)
+            if (o.impurity == impurity && o.block_threads == ctx->block_threads && o.bps_variant == bps_variant && o.n_rows == n_rows &&
+                o.n_cases == max_chunk_cases)
                 resident = o.resident;
-        if (resident == 0) {
+        if (resident == 0 && !fused) {
             WalkParams Wq = W;
+            Wq.n_cases = max_chunk_cases;
             CUDA_TRY(launch_walk(Wq, impurity, ctx->block_threads, bps_variant, 0, s.stream, &resident));
-            if (resident > 0) ctx->occupancy.push_back({impurity, ctx->block_threads, bps_variant, n_rows, resident});
+            if (resident > 0) ctx->occupancy.push_back({impurity, ctx->block_threads, bps_variant, n_rows, max_chunk_cases, resident});
         }
-        if (resident < 1) return fail(MC3D_ECUDA, "walk kernel does not fit on an SM (block %d, rows %d)", ctx->block_threads, n_rows);
-        resident = std::min(resident, bps_variant);
+        if (resident < 1 && !fused)
+            return fail(MC3D_ECUDA, "walk kernel does not fit on an SM (block %d, rows %d, cases %u)", ctx->block_threads, n_rows, max_chunk_cases);
+        resident = std::max(1, std::min(resident, bps_variant));
         if (ctx->blocks_per_sm == 0) {
-            const uint64_t want_blocks = (std::min<uint64_t>(cnt, CHUNK_PHOTONS) / 26 + ctx->block_threads - 1) / ctx->block_threads;
+            const uint64_t per_lane = lone ? 13 : 26;
+            const uint64_t want_blocks = (std::min<uint64_t>(cnt, CHUNK_PHOTONS) / per_lane + ctx->block_threads - 1) / ctx->block_threads;
             const int per_sm = (int)std::min<uint64_t>(resident, std::max<uint64_t>(1, want_blocks / d.sm_count));
             resident = per_sm;
         }
         st.grid_blocks = d.sm_count * resident;
 
+        size_t case_at = 0;
         for (int c = 0; c < n_chunks; ++c) {
             const uint64_t c_off = chunks[c].first;
             const uint32_t c_cnt = chunks[c].second;
             WalkParams Wc = W;
-            Wc.photon_begin = photon_begin + off + c_off;
             Wc.n_photon = c_cnt;
             Wc.rows = d_rows;
+            if (J.sweep) {
+                Wc.n_cases = (uint32_t)(chunk_cases[c].second - chunk_cases[c].first + 1);
+                Wc.case0 = (uint32_t)chunk_cases[c].first;
+                Wc.cases = d_cases + case_at;
+                case_at += Wc.n_cases;
+            } else {
+                const HostCase &hc = J.cases[0];
+                Wc.c = make_devcase(&hc.params, 0, n_rows);
+                Wc.c.id0 = hc.id_begin + J.range_begin + off + c_off;
+            }
             Wc.counter = d_counters + 2 * c;
             Wc.n_fresh = d_counters + 2 * c + 1;
             Wc.fresh = s.fresh.p;
@@ -710,8 +910,10 @@ static int run_async_impl(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, con
             const int want = (int)((c_cnt + ctx->block_threads - 1) / ctx->block_threads);
             const int grid = std::max(1, std::min(st.grid_blocks, want));
             CUDA_TRY(cudaEventRecord(s.ev[2 * c], s.stream));
-            CUDA_TRY(launch_init(Wc, impurity, d.sm_count, s.stream));
-            CUDA_TRY(launch_walk(Wc, impurity, ctx->block_threads, bps_variant, grid, s.stream, nullptr));
+            if (!fused) {
+                CUDA_TRY(launch_init(Wc, impurity, d.sm_count, s.stream));
+                CUDA_TRY(launch_walk(Wc, impurity, ctx->block_threads, bps_variant, grid, s.stream, nullptr));
+            }
             FinalizeParams F;
             memset(&F, 0, sizeof F);
             F.raw = s.raw.p;
@@ -719,8 +921,14 @@ static int run_async_impl(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, con
             F.edges = d_edges;
             F.n_photon = c_cnt;
             F.n_rows = n_rows;
-            F.n_theta_bins = P->n_theta_bins;
-            F.n_phi_bins = P->n_phi_bins;
+            F.n_theta_bins = J.n_theta_bins;
+            F.n_phi_bins = J.n_phi_bins;
+            if (J.sweep) {
+                F.cases = Wc.cases;
+                F.n_cases = Wc.n_cases;
+                F.case0 = Wc.case0;
+                F.case_events = d_case_ev;
+            }
             if (want_rec) {
                 records_layout(c_cnt, rec_off);
                 F.condition = host_col[0] ? s.recs.p + rec_off[0] : nullptr;
@@ -741,7 +949,8 @@ static int run_async_impl(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, con
                 F.path_bins = hs.path_bins;
                 F.path_scale = hs.path_scale;
             }
-            CUDA_TRY(launch_finalize(F, d.sm_count, s.stream));
+            if (fused) CUDA_TRY(launch_fused(Wc, F, impurity, d.sm_count, s.stream));
+            else CUDA_TRY(launch_finalize(F, d.sm_count, s.stream));
             CUDA_TRY(cudaEventRecord(s.ev[2 * c + 1], s.stream));
             if (want_packed) {
                 CUDA_TRY(cudaMemcpyAsync(rec->packed + 4 * (off + c_off), s.recs.p, (size_t)c_cnt * 16, cudaMemcpyDeviceToHost, s.stream));
@@ -761,7 +970,8 @@ static int run_async_impl(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, con
         s.n_photon = cnt;
         s.tally_len = tally_len;
         s.n_chunks = n_chunks;
-        s.user_tally = tally;
+        s.user_tally = J.tally;
+        s.user_case_ev = J.case_events;
         s.packed = want_packed;
     }
 
@@ -779,7 +989,7 @@ static int run_async_impl(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, con
         Device &d = ctx->devs[0];
         Slot &s = d.slot[slot_idx];
         CUDA_TRY(cudaSetDevice(d.id));
-        CUDA_TRY(cudaMemcpyAsync(s.host_acc, s.acc.p, (tally_len + 1 + s.extras_len) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
+        CUDA_TRY(cudaMemcpyAsync(s.host_acc, s.acc.p, (tally_len + 1 + s.extras_len + s.n_case_ev) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
     }
     return MC3D_OK;
 }
@@ -836,6 +1046,14 @@ int mc3d_wait(mc3d_ctx *ctx, int slot_idx, mc3d_stats *stats)
     Slot &s0 = ctx->devs[0].slot[slot_idx];
     st.n_events = s0.host_acc[s0.tally_len];
     if (s0.user_tally) memcpy(s0.user_tally, s0.host_acc, s0.tally_len * sizeof(uint64_t));
+    if (s0.user_case_ev && s0.n_case_ev) {   // events per case: summed over the devices on the host
+        for (size_t c = 0; c < s0.n_case_ev; ++c) s0.user_case_ev[c] = 0;
+        for (Device &d : ctx->devs) {
+            const Slot &s = d.slot[slot_idx];
+            const unsigned long long *ev = s.host_acc + s.tally_len + 1 + s.extras_len;
+            for (size_t c = 0; c < s0.n_case_ev; ++c) s0.user_case_ev[c] += ev[c];
+        }
+    }
     st.kernel_ms = kernel_ms;
     st.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - ctx->t0[slot_idx]).count();
     if (stats) *stats = st;

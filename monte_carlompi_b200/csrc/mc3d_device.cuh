@@ -63,7 +63,7 @@ struct DevRow {
     uint32_t s_last;  // impurity iff species word <= s_last (and s_any)
     uint32_t s_any;   // 0 when P_ext_imp == 0 (species word never selects the impurity)
     float inv_ext;    // ln 2 / (ext_cff_mss rho_snw): metres per unit of the walk's depth scale (optical depth / ln 2)
-    uint32_t pad;
+    float neg_tau_tot;// DevCase::neg_tau_tot of the case the row belongs to (sweep launches read it with the row)
 };
 static_assert(sizeof(DevRow) == 64, "DevRow is 64 bytes");
 constexpr uint32_t RENORM_KEY = 0xffc0u;   // a key16 at/above this also triggers renormalisation (2^-10 per event)
@@ -73,36 +73,54 @@ struct __align__(16) RawResult {
     float ux, uy, uz;   // final direction cosines
     float path_tau;     // path inside the slab in units of ln 2 optical depths (DevRow::inv_ext converts to metres)
     uint32_t n_scat;    // i - 1
-    uint32_t meta;      // condition | row << 8
-    uint32_t pad0, pad1;
+    uint32_t meta;      // condition | row << 8   (row in the launch's table)
+    uint32_t lcase;     // sweep launches: case index in the launch
+    uint32_t pad1;
 };
 
 // A photon that survived its first event, waiting for a lane of the walk kernel (written by the init kernel).
 struct __align__(16) Fresh {
     uint32_t pid;    // photon offset in this launch
-    uint32_t row;    // SSP row
+    uint32_t row;    // SSP row in the launch's table | (case index in the launch) << 12   (sweep launches)
     float dtau;      // free path of the first event
-    uint32_t pad;
+    uint32_t redo;   // != 0: event 1 needed attention and the walk kernel redoes its termination chain (resolve());
+                     // key16 << 16 | impurity << 1 | 1 of that event (walk_device.cuh: first_event)
 };
 
-struct WalkParams {
-    uint32_t rk[2 * PHILOX_ROUNDS];   // Philox round keys: rk[2r], rk[2r+1] for round r
+// Scalars of one case (one MonteCarlo.run: theta_0, tau_tot, the wavelength band, the Lambertian options) as the
+// device code reads them.  A single-case launch carries one in its kernel parameters (constant bank); a sweep launch
+// (mc3d_run_sweep: many cases, one launch, a concatenated SSP table) stages one per case in shared memory and every
+// lane finds its own through the high word of its photon id.
+struct __align__(16) DevCase {
+    uint64_t id0;           // global photon id of the launch's photon 0 under this case's numbering: id = id0 + pid
+    uint32_t pid_first;     // first photon of the case in this launch (cases are contiguous, ascending pid ranges)
+    uint32_t row_begin;     // first SSP row of the case in the launch's table (records hold row - row_begin)
     float mu0x, mu0z;       // sin(theta0), -cos(theta0)
     float neg_tau_tot;      // -tau_tot / ln 2: depths and paths are carried in units of ln 2 optical depths, so that
     float tau_tot;          //  tau_tot / ln 2   a free path is just -log2(u) (no multiply by ln 2 per event)
     double wvl0_x100, sigma_x100;  // wavelength draw in units of 0.01 um
-    int32_t k_first;
-    int32_t n_rows;
     int64_t refl_thr;       // bottom reflects iff (int64)w <= refl_thr  (U(w) <= R)
+    int32_t k_first;
+    int32_t n_rows;         // rows of this case
     uint32_t lambert_bottom;
-    uint32_t refill_threshold;
-    uint32_t lambert_surface;   // run(Lambertian_surface=True): the init kernel finishes every photon by itself
+    uint32_t lambert_surface;   // run(Lambertian_surface=True): the prologue finishes every photon by itself
     uint32_t surf_t16, surf_t24;   // 40-bit threshold of the surface reflectance (ssa_event = R, monte_carlo3D.py:1385-1387)
+};
+static_assert(sizeof(DevCase) == 80, "DevCase is 80 bytes");
+
+struct WalkParams {
+    uint32_t rk[2 * PHILOX_ROUNDS];   // Philox round keys: rk[2r], rk[2r+1] for round r
+    DevCase c;              // the case of a single-case launch (sweep launches: `cases`)
+    int32_t n_rows;         // rows of the launch's table (all cases)
+    uint32_t n_cases;       // sweep launches: cases overlapping this launch (staged in shared memory); else 0
+    uint32_t case0;         // sweep launches: global index of cases[0] (a photon's case index is id >> 40)
+    uint32_t refill_threshold;
     uint32_t drain_give;    // drain phase: a warp with <= this many photons hands them to the block's pool (0 = off)
-    uint64_t photon_begin;  // global id of photon 0 of this launch
+    uint32_t drain_latency; // drain phase: latency-oriented groups (the launch runs alone: its tail is a dependent chain)
     uint32_t n_photon;      // photons in this launch (< 2^31)
     uint32_t pad;
     const DevRow *rows;     // [n_rows], global
+    const DevCase *cases;   // [n_cases], global (sweep launches)
     uint32_t *counter;      // walk kernel: next unclaimed entry of `fresh`
     uint32_t *n_fresh;      // number of entries in `fresh` (appended by the init kernel)
     Fresh *fresh;           // [n_photon]
@@ -135,6 +153,10 @@ struct FinalizeParams {
     int32_t n_scat_bins, path_bins;
     int32_t hist_smem;           // histogram staged in shared memory behind the tally block
     double path_scale;
+    // sweep launches
+    const DevCase *cases;        // [n_cases] or null: records hold row - cases[lcase].row_begin
+    uint32_t n_cases, case0;
+    unsigned long long *case_events;   // [total cases of the call] or null: events per case, index case0 + lcase
 };
 
 // fp64 replay mode (replay_kernel.cu): per-photon inputs exactly as the reference holds them

@@ -32,6 +32,15 @@
 
 namespace mc3d {
 
+#ifdef MC3D_TIMELINE
+// debug build (make timeline): per-warp %globaltimer at kernel entry, at exhaustion of the fresh list and at exit
+__device__ unsigned long long g_timeline[3 * 16384];
+__device__ __forceinline__ unsigned long long now_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define TIMELINE(slot) do { if (lane == 0) { const uint32_t w_ = blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5); if (w_ < 16384u) g_timeline[3 * w_ + (slot)] = now_ns(); } } while (0)
+#else
+#define TIMELINE(slot) do { } while (0)
+#endif
+
 constexpr int RING = 64;  // entries per warp; a refill adds at most 32 to fewer than 32 leftovers
 
 // Fresh photons staged for the lanes of one warp.
@@ -43,7 +52,7 @@ struct WarpRing {
 // only touched under `lock`.  `draining` counts the warps currently in phase B: a warp donates only while another
 // one is there to receive, and no warp leaves while the pool holds photons, so nothing is ever stranded.
 constexpr int POOL_CAP = 64;
-constexpr int POOL_WORDS = 10;   // z, ux, uy, uz, path_lo, path_hi, i, plo, row_addr, blk
+constexpr int POOL_WORDS = 11;   // z, ux, uy, uz, path_lo, path_hi, i, plo, row_addr, blk, phi (sweep launches)
 struct DrainPool {
     uint32_t lock, count, draining, pad;
     uint32_t word[POOL_WORDS][POOL_CAP];
@@ -73,16 +82,18 @@ __device__ __forceinline__ void pool_release(DrainPool &D, uint32_t lane)
 // One warp vote per group of four events: the vote + threshold test costs ~14 issue cycles, and a stopped lane idles
 // at most three events before it is noticed.  (Strongly absorbing or optically thin media, a few events per photon,
 // take the fused one-thread-per-photon kernel instead: fused_kernel.cu.)
-template <bool IMP, int BLOCK, int MIN_BLOCKS>
+// SWEEP: the launch walks photons of several cases (mc3d_run_sweep); a lane then carries the high word of its photon
+// id (which names the case) and reads the slab bottom with its SSP row.  Everything else is the same code.
+template <bool IMP, bool SWEEP, int BLOCK, int MIN_BLOCKS>
 __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) walk_kernel(const __grid_constant__ WalkParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     DevRow *rows = reinterpret_cast<DevRow *>(smem_raw);
-    WarpRing *rings = reinterpret_cast<WarpRing *>(smem_raw + ((P.n_rows * sizeof(DevRow) + 15) & ~size_t(15)));
+    const DevCase *cases = staged_cases(P, smem_raw);
+    WarpRing *rings = reinterpret_cast<WarpRing *>(smem_raw + tables_bytes(P.n_rows, P.n_cases));
     DrainPool &D = *reinterpret_cast<DrainPool *>(rings + BLOCK / 32);
     if (threadIdx.x == 0) { D.lock = 0u; D.count = 0u; D.draining = 0u; D.pad = 0u; }
-    for (int k = threadIdx.x; k < P.n_rows * (int)(sizeof(DevRow) / 4); k += BLOCK)
-        reinterpret_cast<uint32_t *>(rows)[k] = reinterpret_cast<const uint32_t *>(P.rows)[k];
+    stage_tables(P, smem_raw, BLOCK);
     __syncthreads();
 
     const uint32_t lane = threadIdx.x & 31u;
@@ -94,16 +105,17 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) walk_kernel(const __grid_co
 
     Lane L;
     L.z = 0.f; L.ux = 0.f; L.uy = 0.f; L.uz = -1.f; L.path_lo = 0.f; L.path_hi = 0.f;
-    L.i = 0; L.blk = 0; L.plo = 0; L.row_addr = rows_addr; L.key = 0; L.imp = false;
+    L.i = 0; L.blk = 0; L.plo = 0; L.phi = 0; L.row_addr = rows_addr; L.key = 0; L.imp = false;
     L.pk.pB = L.pk.pC = L.pk.pD = 0;
     bool alive = false;   // false: the lane is waiting (its last event needs attention, or it carries no photon)
+    TIMELINE(0);
 
     // ---- phase A: steady state.  Lanes that stop just wait; when `threshold` of them are waiting the warp takes
     // one uniform branch that resolves them together and refills the empty ones from the ring.
     for (;;) {
         const uint32_t waiting = __ballot_sync(0xffffffffu, !alive);
         if (__popc(waiting) >= threshold) {
-            if (!alive && L.i != 0u) alive = resolve_lane<IMP>(P, rows, rows_addr, L);
+            if (!alive && L.i != 0u) alive = resolve_lane<IMP, SWEEP>(P, cases, rows, rows_addr, L);
             const uint32_t empty = __ballot_sync(0xffffffffu, !alive);
             const uint32_t need = __popc(empty);
             bool exhausted = false;
@@ -124,39 +136,52 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) walk_kernel(const __grid_co
                 if (rank < avail) {
                     const uint4 f = Q.entry[(ring_head + rank) & (RING - 1)];
                     const float dtau = __uint_as_float(f.z);
-                    L.plo = (uint32_t)P.photon_begin + f.x;
+                    const DevCase &C = SWEEP ? cases[f.y >> 12] : P.c;
+                    if (SWEEP) {
+                        const uint64_t id = C.id0 + f.x;
+                        L.plo = (uint32_t)id;
+                        L.phi = (uint32_t)(id >> 32);
+                    } else {
+                        L.plo = (uint32_t)C.id0 + f.x;
+                    }
                     L.pk = philox_walk_constants(L.plo, P.rk);
-                    L.row_addr = rows_addr + f.y * (uint32_t)sizeof(DevRow);
+                    L.row_addr = rows_addr + (SWEEP ? f.y & 0xfffu : f.y) * (uint32_t)sizeof(DevRow);
                     L.blk = 0u;
-                    L.ux = P.mu0x; L.uy = 0.0f; L.uz = P.mu0z;
-                    L.z = dtau * P.mu0z;
+                    L.ux = C.mu0x; L.uy = 0.0f; L.uz = C.mu0z;
+                    L.z = __fmul_rn(dtau, C.mu0z);
                     L.path_lo = dtau;
                     L.path_hi = 0.0f;
                     L.i = 1u;
-                    alive = true;
+                    // f.w != 0 (Fresh::redo): event 1 needed attention -- a reflecting Lambertian bottom on the
+                    // first step, or a fine absorption test / renormalisation.  The lane starts out waiting, so the
+                    // next resolve pass redoes that event's chain (same draws, same result)
+                    alive = f.w == 0u;
+                    if (!alive) { L.key = f.w & 0xffff0000u; L.imp = (f.w & 2u) != 0u; }
                 }
             }
             ring_head += min(avail, need);
             __syncwarp();
             if (exhausted) break;   // the ring is empty and the list has been handed out: drain
         }
-        if (alive) alive = group<IMP, false>(P, rows, rows_addr, L);
+        if (alive) alive = group<IMP, false, SWEEP>(P, rows, rows_addr, L);
     }
 
-    // ---- phase B: drain.  Nothing left to hand out; every lane finishes the photon it carries.  The SM empties
-    // out, so this loop is latency-bound: it uses the eager group (the three Philox blocks of a group are independent
-    // multiply chains that overlap the events' arithmetic).  Warps consolidate through the block's pool (see DrainPool).
+    // ---- phase B: drain.  Nothing left to hand out; every lane finishes the photon it carries.  A launch that runs
+    // alone (drain_give == 0) is now bound by the dependent chain of its longest walks: group_latency().  With other
+    // launches in flight the issue slots matter instead: eager group, and the warps consolidate through the block's
+    // pool (see DrainPool).
+    TIMELINE(1);
     if (lane == 0) atomicAdd(&D.draining, 1u);
     const uint32_t give_max = P.drain_give;   // 0: plain drain loop (the launch runs alone)
     // Unlocked peek at the pool: (count << 8) | draining, lane 0's view, so every branch on it is warp-uniform.
     // Refreshed once per iteration, one event stale; every decision is re-made under the lock.
     uint32_t peek = 0u;
     for (;;) {
-        if (!alive && L.i != 0u) alive = resolve_lane<IMP>(P, rows, rows_addr, L);
+        if (!alive && L.i != 0u) alive = resolve_lane<IMP, SWEEP>(P, cases, rows, rows_addr, L);
         const uint32_t alive_mask = __ballot_sync(0xffffffffu, alive);
         const uint32_t n_alive = __popc(alive_mask);
         if (give_max == 0u) {
-            if (n_alive == 0u) break;
+            if (n_alive == 0u) { TIMELINE(2); break; }
         } else if (n_alive < 32u) {
             const bool take = (peek >> 8) != 0u;
             const bool give = !take && n_alive != 0u && n_alive <= give_max && (peek & 0xffu) > 1u;
@@ -175,6 +200,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) walk_kernel(const __grid_co
                         L.path_hi = __uint_as_float(pool_get(&D.word[5][e]));
                         L.i = pool_get(&D.word[6][e]); L.plo = pool_get(&D.word[7][e]); L.row_addr = pool_get(&D.word[8][e]);
                         L.blk = pool_get(&D.word[9][e]);
+                        if (SWEEP) L.phi = pool_get(&D.word[10][e]);
                         taken = true;
                     }
                     __syncwarp();
@@ -192,12 +218,13 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) walk_kernel(const __grid_co
                         pool_put(&D.word[5][e], __float_as_uint(L.path_hi));
                         pool_put(&D.word[6][e], L.i); pool_put(&D.word[7][e], L.plo); pool_put(&D.word[8][e], L.row_addr);
                         pool_put(&D.word[9][e], L.blk);
+                        if (SWEEP) pool_put(&D.word[10][e], L.phi);
                     }
                     if (lane == 0) { pool_put(&D.count, c + n_alive); atomicSub(&D.draining, 1u); }
                     leave = true;
                 }
                 pool_release(D, lane);
-                if (leave) break;
+                if (leave) { TIMELINE(2); break; }
                 if (taken) {   // outside the lock: rebuild the Philox state of the photon just taken over
                     L.pk = philox_walk_constants(L.plo, P.rk);
                     alive = true;
@@ -206,22 +233,29 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) walk_kernel(const __grid_co
         }
         if (give_max != 0u)
             peek = __shfl_sync(0xffffffffu, lane == 0 ? (pool_get(&D.count) << 8) | min(pool_get(&D.draining), 255u) : 0u, 0);
-        if (alive) alive = group<IMP, true>(P, rows, rows_addr, L);
+        if (alive) alive = P.drain_latency ? group_latency<IMP, SWEEP>(P, rows, rows_addr, L) : group<IMP, true, SWEEP>(P, rows, rows_addr, L);
     }
 }
 
+#ifdef MC3D_TIMELINE
+extern "C" int mc3d_debug_timeline(unsigned long long *out, int n_words)
+{
+    return (int)cudaMemcpyFromSymbol(out, g_timeline, sizeof(unsigned long long) * (size_t)n_words);
+}
+#endif
+
 // ---- launch helper (called from the host runtime) ------------------------------------------------------------
 
-size_t walk_smem_bytes(int n_rows, int block_threads)
+size_t walk_smem_bytes(int n_rows, uint32_t n_cases, int block_threads)
 {
-    return ((n_rows * sizeof(DevRow) + 15) & ~size_t(15)) + (block_threads / 32) * sizeof(WarpRing) + sizeof(DrainPool);
+    return tables_bytes(n_rows, n_cases) + (block_threads / 32) * sizeof(WarpRing) + sizeof(DrainPool);
 }
 
-template <bool IMP, int BLOCK, int MIN_BLOCKS>
+template <bool IMP, bool SWEEP, int BLOCK, int MIN_BLOCKS>
 static cudaError_t launch_one(const WalkParams &P, int grid, cudaStream_t stream, int *occupancy)
 {
-    const size_t smem = walk_smem_bytes(P.n_rows, BLOCK);
-    auto kern = walk_kernel<IMP, BLOCK, MIN_BLOCKS>;
+    const size_t smem = walk_smem_bytes(P.n_rows, P.n_cases, BLOCK);
+    auto kern = walk_kernel<IMP, SWEEP, BLOCK, MIN_BLOCKS>;
     if (smem > 48 * 1024) {   // only large SSP tables need the opt-in (the default table + rings + pool is ~14 KB)
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -234,8 +268,12 @@ static cudaError_t launch_one(const WalkParams &P, int grid, cudaStream_t stream
 template <int BLOCK, int MIN_BLOCKS>
 static cudaError_t launch_variant(const WalkParams &P, bool impurity, int grid, cudaStream_t stream, int *occupancy)
 {
-    if (impurity) return launch_one<true, BLOCK, MIN_BLOCKS>(P, grid, stream, occupancy);
-    return launch_one<false, BLOCK, MIN_BLOCKS>(P, grid, stream, occupancy);
+    if (P.n_cases) {
+        if (impurity) return launch_one<true, true, BLOCK, MIN_BLOCKS>(P, grid, stream, occupancy);
+        return launch_one<false, true, BLOCK, MIN_BLOCKS>(P, grid, stream, occupancy);
+    }
+    if (impurity) return launch_one<true, false, BLOCK, MIN_BLOCKS>(P, grid, stream, occupancy);
+    return launch_one<false, false, BLOCK, MIN_BLOCKS>(P, grid, stream, occupancy);
 }
 
 // block_threads in {128, 256, 512}; blocks_per_sm is the occupancy target the variant is compiled for (64 / 48

@@ -15,7 +15,8 @@ N_COND = 8
 N_SLOTS = 16
 FLAG_LAMBERT_BOTTOM = 1
 FLAG_LAMBERT_SURFACE = 2
-ABI_VERSION = 2
+ABI_VERSION = 3
+PATH_AUTO, PATH_FUSED, PATH_PERSISTENT = 0, 1, 2
 PACKED_MAX_ROWS = 512          # packed 16-byte records hold the SSP row in 9 bits
 PACKED_NSCAT_MAX = 0x7fffff    # ... and n_scat in 23 bits (saturating; Stats.packed_saturated reports it)
 
@@ -23,7 +24,7 @@ EXPORTS = ('mc3d_abi_version', 'mc3d_last_error', 'mc3d_query', 'mc3d_create', '
            'mc3d_create_rank', 'mc3d_destroy', 'mc3d_host_alloc', 'mc3d_host_free', 'mc3d_run', 'mc3d_run_async',
            'mc3d_wait', 'mc3d_reduce_tally', 'mc3d_replay', 'mc3d_set_launch', 'mc3d_write_records_text', 'mc3d_py_repr',
            'mc3d_set_histograms', 'mc3d_get_histograms', 'mc3d_records_layout', 'mc3d_set_input_caching',
-           'mc3d_unpack_records')
+           'mc3d_unpack_records', 'mc3d_set_walk_path', 'mc3d_run_sweep', 'mc3d_run_sweep_async')
 
 
 class Mc3dError(RuntimeError):
@@ -42,6 +43,15 @@ class Params(C.Structure):
         return N_COND + self.n_theta_bins * max(1, self.n_phi_bins)
 
 
+class SweepCase(C.Structure):
+    """mc3d_sweep_case: one case of a sweep -- its scalars, its rows in the concatenated table, its photon count."""
+    _fields_ = [('params', Params), ('row_begin', C.c_int32), ('n_rows', C.c_int32), ('n_photon', C.c_uint64)]
+
+
+SWEEP_MAX_CASES = 1024
+SWEEP_ID_SHIFT = 40            # photon j of case c is photon id (c << 40) + j
+
+
 class Records(C.Structure):
     _fields_ = [('condition', C.c_void_p), ('wvl_row', C.c_void_p), ('theta_n', C.c_void_p),
                 ('phi_n', C.c_void_p), ('n_scat', C.c_void_p), ('path_length', C.c_void_p), ('packed', C.c_void_p)]
@@ -57,7 +67,7 @@ class Stats(C.Structure):
     _fields_ = [('n_photon', C.c_uint64), ('n_events', C.c_uint64), ('kernel_ms', C.c_double),
                 ('total_ms', C.c_double), ('n_devices', C.c_int32), ('sm_count', C.c_int32),
                 ('sm_clock_khz', C.c_int32), ('grid_blocks', C.c_int32), ('block_threads', C.c_int32),
-                ('packed_saturated', C.c_int32)]
+                ('packed_saturated', C.c_int32), ('walk_path', C.c_int32), ('reserved', C.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -116,6 +126,9 @@ def load_library():
     lib.mc3d_set_input_caching.argtypes = [vp, i32]
     lib.mc3d_get_histograms.argtypes = [vp, i32, vp, vp, vp]
     lib.mc3d_unpack_records.argtypes = [vp, u64, vp, i32]
+    lib.mc3d_set_walk_path.argtypes = [vp, i32]
+    lib.mc3d_run_sweep.argtypes = [vp, vp, i32, vp, i32, u64, vp, vp, vp, vp]
+    lib.mc3d_run_sweep_async.argtypes = [vp, i32, vp, i32, vp, i32, u64, u64, u64, vp, vp, vp]
     if lib.mc3d_abi_version() != ABI_VERSION:
         raise Mc3dError('libmc3d.so ABI %d != expected %d' % (lib.mc3d_abi_version(), ABI_VERSION))
     _lib = lib
@@ -296,6 +309,12 @@ class Context(object):
         """Skip (default) or force the upload of inputs identical to the slot's previous call."""
         _check(self._lib.mc3d_set_input_caching(self._ctx, 1 if enabled else 0))
 
+    def set_walk_path(self, path=PATH_AUTO):
+        """PATH_AUTO (default), PATH_FUSED (one kernel, short walks) or PATH_PERSISTENT (three kernels, long walks);
+        also accepts 'auto' / 'fused' / 'persistent'.  A performance choice: the results are bit-identical."""
+        path = {'auto': PATH_AUTO, 'fused': PATH_FUSED, 'persistent': PATH_PERSISTENT}.get(path, path)
+        _check(self._lib.mc3d_set_walk_path(self._ctx, int(path)))
+
     def set_launch(self, blocks_per_sm=0, block_threads=0, refill_threshold=0):
         _check(self._lib.mc3d_set_launch(self._ctx, blocks_per_sm, block_threads, refill_threshold))
 
@@ -352,6 +371,76 @@ class Context(object):
         _check(self._lib.mc3d_run_async(self._ctx, slot, C.byref(params), _ptr(table), len(table), int(seed),
                                         int(photon_begin), int(n_photon),
                                         C.byref(rec_struct) if rec_struct is not None else None, _ptr(tally), None))
+
+    def run_sweep_async(self, slot, cases, table, seed, records=None, tally=None, case_events=None, range_begin=0,
+                        range_count=None):
+        """Enqueue a sweep: ``cases`` is a list of (Params, row_begin, n_rows, n_photon) over the concatenated ``table``;
+        photon j of case c is photon id (c << 40) + j of the stream ``seed`` (mc3d_run_sweep in include/mc3d.h).
+        ``records``: RecordBuffers / packed uint32 array / dict of columns for the photons of
+        [range_begin, range_begin + range_count) in case order, or None; ``tally``: uint64 (len(table), tally_width);
+        ``case_events``: uint64 (len(cases),) or None.  Finish with ``wait(slot)``."""
+        table = np.ascontiguousarray(table, dtype=ROW_DTYPE)
+        arr = (SweepCase * len(cases))()
+        total = 0
+        for k, (prm, row_begin, n_rows, n) in enumerate(cases):
+            arr[k].params = prm
+            arr[k].row_begin, arr[k].n_rows, arr[k].n_photon = int(row_begin), int(n_rows), int(n)
+            total += int(n)
+        if range_count is None:
+            range_count = total - int(range_begin)
+        rec_struct = None
+        if isinstance(records, RecordBuffers):
+            rec_struct = records.struct_for(range_count)
+        elif isinstance(records, np.ndarray):
+            assert records.dtype == np.uint32 and records.flags.c_contiguous and records.size >= 4 * int(range_count)
+            rec_struct = Records(None, None, None, None, None, None, records.ctypes.data)
+        elif records is not None:
+            rec_struct = Records(*[records[name].ctypes.data if records.get(name) is not None else None
+                                   for name, _ in RECORD_COLUMNS], None)
+        if tally is not None:
+            assert tally.dtype == np.uint64 and tally.flags.c_contiguous
+            assert tally.size == len(table) * cases[0][0].tally_width
+        if case_events is not None:
+            assert case_events.dtype == np.uint64 and case_events.flags.c_contiguous and case_events.size == len(cases)
+        self._keep[slot] = (arr, table, rec_struct, records, tally, case_events)
+        _check(self._lib.mc3d_run_sweep_async(self._ctx, int(slot), arr, len(cases), _ptr(table), len(table), int(seed),
+                                              int(range_begin), int(range_count),
+                                              C.byref(rec_struct) if rec_struct is not None else None, _ptr(tally),
+                                              _ptr(case_events)))
+
+    def run_sweep(self, cases, table, seed, records=True, tally=True):
+        """Synchronous sweep.  Returns (list of per-case record dicts or None, tally or None, events per case, stats)."""
+        table = np.ascontiguousarray(table, dtype=ROW_DTYPE)
+        total = sum(int(c[3]) for c in cases)
+        packed = bool(records) and all(int(c[2]) <= PACKED_MAX_ROWS for c in cases)
+        rec = None
+        if packed:
+            rec = np.empty(4 * max(total, 1), np.uint32)
+        elif records:
+            rec = {name: np.empty(total, dtype=dt) for name, dt in RECORD_COLUMNS}
+        t = np.zeros((len(table), cases[0][0].tally_width), np.uint64) if tally else None
+        ev = np.zeros(len(cases), np.uint64)
+        self.run_sweep_async(0, cases, table, seed, rec, t, ev)
+        stats = self.wait(0)
+        per_case = None
+        if records:
+            if packed and stats['packed_saturated']:
+                return self._sweep_columns(cases, table, seed, tally)
+            cols = unpack_records(rec, total) if packed else rec
+            edges = np.cumsum([0] + [int(c[3]) for c in cases])
+            per_case = [{k: v[edges[i]:edges[i + 1]] for k, v in cols.items()} for i in range(len(cases))]
+        return per_case, t, ev, stats
+
+    def _sweep_columns(self, cases, table, seed, tally):
+        """A sweep whose packed records saturated (a walk beyond 2^23 scatterings): fetch the six columns instead."""
+        total = sum(int(c[3]) for c in cases)
+        rec = {name: np.empty(total, dtype=dt) for name, dt in RECORD_COLUMNS}
+        t = np.zeros((len(table), cases[0][0].tally_width), np.uint64) if tally else None
+        ev = np.zeros(len(cases), np.uint64)
+        self.run_sweep_async(0, cases, table, seed, rec, t, ev)
+        stats = self.wait(0)
+        edges = np.cumsum([0] + [int(c[3]) for c in cases])
+        return [{k: v[edges[i]:edges[i + 1]] for k, v in rec.items()} for i in range(len(cases))], t, ev, stats
 
     def wait(self, slot):
         st = Stats()

@@ -37,6 +37,10 @@ CASES = {
     'impurity': (30., 3.0, 0.5, True, ('spectral', 100, 104, 156, 1e-5), 1.3, SIGMA13, 104),
     'bright_bottom_R1': (15., 1.0, 1.0, True, ('spectral', 100, 104, 156, 0.0), 1.3, SIGMA13, 104),
     'wide_band_clamped_table': (15., 4.0, 0.3, True, ('spectral', 100, 20, 45, 0.0), 0.33, 0.26 / 2.355, 20),
+    # config C3's absorption-terminated corner: 2.1 um, 1000 um grains (about two events per photon)
+    'nir_large_grains_short_walks': (30., 1e6, 0.5, True, ('spectral', 1000, 184, 236, 0.0), 2.1, SIGMA13, 184),
+    # thin slab over a perfectly reflecting Lambertian bottom: most photons reach it on their FIRST step
+    'thin_slab_mirror_bottom': (15., 0.3, 1.0, True, ('spectral', 100, 64, 116, 0.0), 0.9, SIGMA13, 64),
 }
 
 
@@ -48,6 +52,19 @@ def test_same_philox_stream_as_oracle(name):
     Pe, Po = gpu_util.both_params(th, tau, R, wvl0, sig, k0, lb)
     n, seed, begin = 200000, 20190603, 12345
     rec, tally, st = _run(Pe, rows, seed, begin, n)
+    # both kernel paths (the one-kernel short-walk path and the persistent three-kernel path) walk every case:
+    # bit-identical records, tallies and event counts, whichever the library would pick by itself
+    ctx = gpu_util.context()
+    try:
+        for path in ('fused', 'persistent'):
+            ctx.set_walk_path(path)
+            rec2, tally2, st2 = _run(Pe, rows, seed, begin, n)
+            assert st2['walk_path'] == {'fused': engine.PATH_FUSED, 'persistent': engine.PATH_PERSISTENT}[path]
+            for col in rec:
+                assert np.array_equal(rec[col], rec2[col]), (path, col)
+            assert np.array_equal(tally, tally2) and st2['n_events'] == st['n_events'], path
+    finally:
+        ctx.set_walk_path('auto')
     o = oracle.philox(Po, rows, seed, begin, n, n_threads=os.cpu_count())
     same = (rec['condition'] == o['condition']) & (rec['n_scat'] == o['n_scat']) & (rec['wvl_row'] == o['wvl_row'])
     # fp32 vs fp64 flips a branch for a few photons per 10^5 (rint at a wavelength bin edge, z within an ulp of 0)

@@ -11,7 +11,7 @@ __global__ void __launch_bounds__(256, 4) hot(const __grid_constant__ WalkParams
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     DevRow *rows = reinterpret_cast<DevRow *>(smem_raw);
-    for (int k = threadIdx.x; k < P.n_rows * (int)(sizeof(DevRow) / 4); k += 256)
+    for (int k = threadIdx.x; k < P.n_rows * (int)(sizeof(DevRow) / 4); k += blockDim.x)
         reinterpret_cast<uint32_t *>(rows)[k] = reinterpret_cast<const uint32_t *>(P.rows)[k];
     __syncthreads();
     const uint32_t rows_addr = shared_address(rows);
@@ -22,8 +22,8 @@ __global__ void __launch_bounds__(256, 4) hot(const __grid_constant__ WalkParams
     L.pk = philox_walk_constants(L.plo, P.rk);
     uint32_t stops = 0;
     for (uint32_t it = 0; it < iters; ++it) {          // one group = four events per iteration
-        if (MODE == 0 || MODE == 3) {
-            const bool alive = MODE == 0 ? group<false, false>(P, rows, rows_addr, L) : group<false, true>(P, rows, rows_addr, L);
+        if (MODE == 0 || MODE == 3 || MODE == 4) {
+            const bool alive = MODE == 0 ? group<false, false>(P, rows, rows_addr, L) : MODE == 3 ? group<false, true>(P, rows, rows_addr, L) : group_latency<false>(P, rows, rows_addr, L);
             stops += alive ? 0u : 1u;
             if (L.z > -10.0f) L.z -= 40.0f;     // keep the photon deep inside: never exits
         } else if (MODE == 1) {                   // Philox only: three blocks
@@ -56,7 +56,19 @@ int main()
     float *out; cudaMalloc(&out, 148 * 4 * 256 * sizeof(float));
     const uint32_t iters = 5000;
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    const char *names[4] = {"group() full hot loop", "3 x philox_walk only", "4 x scatter_and_move only", "group() eager blocks"};
+    const char *names[5] = {"group() full hot loop", "3 x philox_walk only", "4 x scatter_and_move only", "group() eager blocks", "group_latency()"};
+    // latency: ONE warp per scheduler (148 blocks x 128 threads), the regime of a launch's tail
+    for (int mode : {0, 3, 4}) {
+        auto launch = [&](uint32_t n) {
+            if (mode == 0) hot<0><<<148, 128, sizeof h>>>(P, n, out);
+            else if (mode == 3) hot<3><<<148, 128, sizeof h>>>(P, n, out);
+            else hot<4><<<148, 128, sizeof h>>>(P, n, out);
+        };
+        launch(100);
+        cudaEventRecord(e0); launch(iters); cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        printf("%-26s 1 warp/SMSP (latency): %.1f cycles per event\n", names[mode], ms * 1e-3 * 1.965e9 / (iters * 4.0));
+    }
     for (int bps = 1; bps <= 4; ++bps) for (int mode = 0; mode < 4; ++mode) {
         auto launch = [&](uint32_t n) {
             if (mode == 0) hot<0><<<148 * bps, 256, sizeof h>>>(P, n, out);
