@@ -205,7 +205,7 @@ class MonteCarlo(object):
     # ---- the run (monte_carlo3D.py:1492-1657) -----------------------------------------------------------------
     def run(self, n_photon, wvl0, half_width, rds_snw, theta_0=0., stokes_params=np.array([1, 0, 0, 0]),
             shape='sphere', roughness='smooth', test=False, debug=False, Lambertian_surface=False,
-            Lambertian_bottom=True, Lambertian_reflectance=1., seed=None, write_output=True):
+            Lambertian_bottom=True, Lambertian_reflectance=1., seed=None, write_output=True, first_photon_id=0):
         """ Run the Monte Carlo model given a normal distribution of wavelengths [um].
             ALL VALUES IN MICRONS
 
@@ -213,6 +213,8 @@ class MonteCarlo(object):
             <run>.npz (record columns, per-row wvn / snow depth, tallies, SSP table; output.load_run reads either);
             'binary' = the sidecar only (19 B instead of ~100 B per photon); False = nothing (results stay in
             self.last_records / self.last_tally).
+            first_photon_id: id of photon 0 in the random stream ``seed`` (photon j is photon first_photon_id + j);
+            case c of ``run_sweep`` is ``run(..., first_photon_id=c << 40)``.
         """
         params, table = self._setup_case(n_photon, wvl0, half_width, rds_snw, theta_0, stokes_params, shape, roughness,
                                          test, debug, Lambertian_surface, Lambertian_bottom, Lambertian_reflectance,
@@ -223,8 +225,9 @@ class MonteCarlo(object):
             par = self._parallel = Parallel(n_photon, devices=self.devices)
         begin, count = par._map(n_photon)
         ctx = par.open()
+        self.last_seed = par.broadcast_seed(self.last_seed)         # one stream for all ranks (rank 0's, if from entropy)
         tally = np.zeros((len(table), params.tally_width), np.uint64)
-        records, stats = self._walk_records(ctx, params, table, self.last_seed, begin, count, tally)
+        records, stats = self._walk_records(ctx, params, table, self.last_seed, int(first_photon_id) + begin, count, tally)
         if par.size > 1:
             ctx.reduce_tally(tally, root=0)
         self.last_table, self.last_stats = table, stats
@@ -233,17 +236,22 @@ class MonteCarlo(object):
         if all_answers is None:
             return                                                  # not the root rank
         self.last_records, self.last_tally = all_answers, tally
+        self._write(write_output, all_answers, tally, table, self.snow_depth, n_photon, wvl0, half_width)
+
+    def _write(self, write_output, records, tally, table, snow_depth, n_photon, wvl0, half_width):
+        """The output step of ``run`` (monte_carlo3D.py:1621-1648) for one case; returns the path printed (None when
+        ``write_output`` is False)."""
         if not write_output:
-            return
+            return None
         output_file = self.setup_output(n_photon, wvl0, half_width)
         if write_output != 'binary':
-            output.write_run(output_file, all_answers, 1. / table['wvl_um'], self.snow_depth)
+            output.write_run(output_file, records, 1. / table['wvl_um'], snow_depth)
         if write_output in ('both', 'binary'):
-            sidecar = output.write_sidecar(output_file, all_answers, 1. / table['wvl_um'], self.snow_depth, tally=tally,
-                                           table=table)
+            sidecar = output.write_sidecar(output_file, records, 1. / table['wvl_um'], snow_depth, tally=tally, table=table)
             if write_output == 'binary':
                 output_file = sidecar
         print('%s' % output_file)   # for easy post processing
+        return output_file
 
     def _walk_records(self, ctx, params, table, seed, begin, count, tally):
         """One synchronous walk returning (record columns, stats).  The records come back packed (16 B per photon) into
@@ -262,78 +270,140 @@ class MonteCarlo(object):
         ctx.run_async(0, params, table, seed, begin, count, records, tally)
         return records, ctx.wait(0)
 
-    # ---- batched sweeps (reference monte_carlo3D-run.py:60-96, 112-122: one run() per wavelength / grain size) -----
+    # ---- sweeps (reference monte_carlo3D-run.py:60-96, 112-122: one run() per wavelength / grain size / angle) -------
+    SWEEP_MAX_ROWS = 640            # rows of a batch's concatenated table (40 KB of shared memory per block)
+    SWEEP_MAX_CASES = 128           # cases per batch
+    SWEEP_MAX_PHOTONS = 1 << 27     # photons per batch (2 GiB of packed records in page-locked memory)
+
     def run_sweep(self, cases, write_output=True, seed=None):
-        """Run many cases with up to eight of them in flight on the GPU(s).
+        """Run many cases -- the loops of the reference's driver script over wavelength, grain size and zenith angle --
+        with the SAME launches: the cases of a batch share one concatenated SSP table and their photons are walked
+        together (libmc3d's mc3d_run_sweep), so a short case does not pay a launch and its tail, and long and short
+        cases fill the GPU together.  Batches are pipelined on the context's slots: the copy-back and the text
+        formatting of one overlap the walk of the next.
 
         ``cases``: iterable of dicts with the arguments of ``run`` (``n_photon, wvl0, half_width, rds_snw`` and
-        optionally ``theta_0, Lambertian_bottom, Lambertian_reflectance, Lambertian_surface, test, seed, shape,
-        roughness``).  The
-        reference's sweep drivers call ``run`` once per (wavelength, grain size); here each case is enqueued on its
-        own slot / CUDA stream, so the long-walk tail, the copy-back and the text formatting of one case overlap
-        the walks of the next ones.  Results are identical to calling ``run`` case by case with the same seeds.
-        Returns the list of output paths (or of (records, tally, table) tuples when ``write_output`` is False)."""
+        optionally ``theta_0, Lambertian_bottom, Lambertian_reflectance, Lambertian_surface, test, shape, roughness,
+        seed``).  All cases use one random stream ``seed`` (argument, else the instance's, else OS entropy): photon j
+        of case c is photon ``(c << 40) + j`` of it, i.e. case c is bit-identical to
+        ``run(..., seed=seed, first_photon_id=c << 40)``.  (A case dict with its own ``seed`` starts a new batch; its
+        photon ids still carry its case index.)
+
+        Returns one entry per case, on the root rank (``None`` per case on the other ranks of a one-process-per-GPU
+        launch): the output path when ``write_output`` is set (True | 'both' | 'binary', as in ``run``), else
+        ``(records, tally, table)``."""
         cases = [dict(c) for c in cases]
         if not cases:
             return []
+        if seed is None:
+            seed = self.seed
+        if seed is None:
+            seed = int.from_bytes(os.urandom(8), 'little')
         par = self._parallel
         if par is None:
             par = self._parallel = Parallel(cases[0]['n_photon'], devices=self.devices)
-        if par.size > 1:
-            return [self._run_case_serial(c, write_output, seed) for c in cases]     # one process per GPU: no slots
+        seed = par.broadcast_seed(int(seed))
+        self.last_seed = int(seed)
         ctx = par.open()
-        depth = min(8, engine.N_SLOTS, len(cases))      # each case in flight holds its own pinned record buffers
-        n_max = max(int(c['n_photon']) for c in cases)
-        bufs = [engine.RecordBuffers(n_max) for _ in range(depth)]
-        pending = [None] * depth
+
+        # ---- per-case inputs; cases with the same optics share their rows
+        prepared = []
+        for k, c in enumerate(cases):
+            shape = c.get('shape', 'sphere')
+            if shape != 'sphere' and not self.HG:
+                raise NotImplementedError('aspherical shapes need HG=True (see run)')
+            key = (c['wvl0'], c['half_width'], c['rds_snw'], shape, c.get('roughness', 'smooth'), bool(c.get('test', False)))
+            table, k_first, scale = self.build_table(c['wvl0'], c['half_width'], c['rds_snw'], test=c.get('test', False),
+                                                     shape=shape, roughness=c.get('roughness', 'smooth'))
+            params = engine.make_params((np.pi * c.get('theta_0', 0.)) / 180., self.tau_tot, self.rho_snw,
+                                        c.get('Lambertian_reflectance', 1.), c['wvl0'], scale, k_first,
+                                        lambert_bottom=bool(c.get('Lambertian_bottom', True)),
+                                        lambert_surface=bool(c.get('Lambertian_surface', False)),
+                                        n_theta_bins=int(self.n_theta_bins), n_phi_bins=int(self.n_phi_bins))
+            prepared.append(dict(k=k, c=c, key=key, table=table, params=params, n=int(c['n_photon']),
+                                 seed=int(c.get('seed', seed)), r_eff=self.snow_effective_radius,
+                                 dirs=(getattr(self, 'shape_dir', None), getattr(self, 'roughness_dir', None))))
+
+        # ---- batches: consecutive cases, one seed, bounded table / case count / photons
+        batches, cur = [], None
+        for q in prepared:
+            new_rows = 0 if cur is not None and q['key'] in cur['row_of'] else len(q['table'])
+            if (cur is None or q['seed'] != cur['seed'] or cur['rows'] + new_rows > self.SWEEP_MAX_ROWS or
+                    len(cur['cases']) >= self.SWEEP_MAX_CASES or cur['photons'] + q['n'] > self.SWEEP_MAX_PHOTONS):
+                cur = dict(seed=q['seed'], rows=0, photons=0, cases=[], row_of={}, tables=[])
+                batches.append(cur)
+                new_rows = len(q['table'])
+            if q['key'] not in cur['row_of']:
+                cur['row_of'][q['key']] = cur['rows']
+                cur['tables'].append(q['table'])
+                cur['rows'] += new_rows
+            q['row_begin'] = cur['row_of'][q['key']]
+            cur['cases'].append(q)
+            cur['photons'] += q['n']
+
         results = [None] * len(cases)
+        depth = max(1, min(3, engine.N_SLOTS, len(batches)))
+        cap = max(max(b['photons'] for b in batches), 1)
+        bufs = [engine.RecordBuffers(-(-cap // par.size) + 1) for _ in range(depth)]
+        pending = [None] * depth
+
+        def launch(slot, b):
+            table = np.concatenate(b['tables'])
+            # the engine numbers a sweep's cases from 0: a batch that starts at case k0 of the call pads with empty
+            # cases so that photon ids keep the case's index in the whole call
+            k0 = b['cases'][0]['k']
+            spec = [(b['cases'][0]['params'], 0, len(b['cases'][0]['table']), 0)] * k0
+            spec += [(q['params'], q['row_begin'], len(q['table']), q['n']) for q in b['cases']]
+            total = b['photons']
+            begin, count = par._map(total)
+            tally = np.zeros((len(table), b['cases'][0]['params'].tally_width), np.uint64)
+            events = np.zeros(len(spec), np.uint64)
+            ctx.run_sweep_async(slot, spec, table, b['seed'], bufs[slot], tally, events, range_begin=begin, range_count=count)
+            pending[slot] = (b, table, tally, events, begin, count, k0)
 
         def finish(slot):
-            k, c, table, tally, n, r_eff, dirs = pending[slot]
-            stats = ctx.wait(slot)
-            rec = bufs[slot].view(n)
-            depth_m = ssp.snow_depth(table, self.tau_tot, self.rho_snw)
-            self.last_records, self.last_tally, self.last_table, self.last_stats = rec, tally, table, stats
-            if write_output:
-                self.snow_effective_radius = r_eff
-                self.shape = c.get('shape', 'sphere')
-                self.shape_dir, self.roughness_dir = dirs
-                self.theta_0 = (np.pi * c.get('theta_0', 0.)) / 180.
-                path = self.setup_output(n, c['wvl0'], c['half_width'])
-                output.write_run(path, rec, 1. / table['wvl_um'], depth_m)
-                print('%s' % path)
-                results[k] = path
-            else:
-                results[k] = (rec, tally, table)
+            b, table, tally, events, begin, count, k0 = pending[slot]
             pending[slot] = None
+            stats = ctx.wait(slot)
+            if stats['packed_saturated']:
+                raise engine.Mc3dError('a walk of this sweep exceeded 2^23 scatterings: run that case with run()')
+            rec = bufs[slot].view(count)
+            if par.size > 1:
+                ctx.reduce_tally(tally, root=0)
+                ctx.reduce_tally(events, root=0)
+            rec = par.answer_and_reduce(rec, MonteCarlo.flatten_list)
+            self.last_stats = stats
+            if rec is None:
+                return                                              # not the root rank
+            at = 0
+            for q in b['cases']:
+                r = {name: col[at:at + q['n']] for name, col in rec.items()}
+                at += q['n']
+                t = tally[q['row_begin']:q['row_begin'] + len(q['table'])].copy()
+                shared = sum(1 for o in b['cases'] if o['row_begin'] == q['row_begin'])
+                if shared > 1:                                      # cases that share rows share those tally rows too:
+                    t = _tally_of_records(r, len(q['table']), q['params'])   # rebuild this case's own from its records
+                c = q['c']
+                depth_m = ssp.snow_depth(q['table'], self.tau_tot, self.rho_snw)
+                self.last_records, self.last_tally, self.last_table = r, t, q['table']
+                if write_output:
+                    self.snow_effective_radius = q['r_eff']
+                    self.shape = c.get('shape', 'sphere')
+                    self.shape_dir, self.roughness_dir = q['dirs']
+                    self.theta_0 = (np.pi * c.get('theta_0', 0.)) / 180.
+                    results[q['k']] = self._write(write_output, r, t, q['table'], depth_m, q['n'], c['wvl0'], c['half_width'])
+                else:
+                    results[q['k']] = (r, t, q['table'])
 
         try:
-            for k, c in enumerate(cases):
-                slot = k % depth
+            for j, b in enumerate(batches):
+                slot = j % depth
                 if pending[slot] is not None:
                     finish(slot)
-                n = int(c['n_photon'])
-                shape = c.get('shape', 'sphere')
-                if shape != 'sphere' and not self.HG:
-                    raise NotImplementedError('aspherical shapes need HG=True (see run)')
-                table, k_first, scale = self.build_table(c['wvl0'], c['half_width'], c['rds_snw'], test=c.get('test', False),
-                                                         shape=shape, roughness=c.get('roughness', 'smooth'))
-                r_eff = self.snow_effective_radius
-                dirs = (getattr(self, 'shape_dir', None), getattr(self, 'roughness_dir', None))
-                s = c.get('seed', seed if seed is not None else self.seed)
-                if s is None:
-                    s = int.from_bytes(os.urandom(8), 'little')
-                params = engine.make_params((np.pi * c.get('theta_0', 0.)) / 180., self.tau_tot, self.rho_snw,
-                                            c.get('Lambertian_reflectance', 1.), c['wvl0'], scale, k_first,
-                                            lambert_bottom=bool(c.get('Lambertian_bottom', True)),
-                                            lambert_surface=bool(c.get('Lambertian_surface', False)),
-                                            n_theta_bins=int(self.n_theta_bins), n_phi_bins=int(self.n_phi_bins))
-                tally = np.zeros((len(table), params.tally_width), np.uint64)
-                ctx.run_async(slot, params, table, int(s), 0, n, bufs[slot], tally)
-                pending[slot] = (k, c, table, tally, n, r_eff, dirs)
-            for slot in sorted(range(depth), key=lambda sl: pending[sl][0] if pending[sl] else -1):
-                if pending[slot] is not None:
-                    finish(slot)
+                launch(slot, b)
+            for j in range(len(batches) - depth, len(batches)):
+                if j >= 0 and pending[j % depth] is not None:
+                    finish(j % depth)
         finally:
             for slot in range(depth):
                 if pending[slot] is not None:
@@ -341,15 +411,9 @@ class MonteCarlo(object):
                         ctx.wait(slot)
                     except engine.Mc3dError:
                         pass
-            for b in bufs:
-                b.free()
+            for buf in bufs:
+                buf.free()
         return results
-
-    def _run_case_serial(self, c, write_output, seed):
-        kw = {k: v for k, v in c.items() if k not in ('n_photon', 'wvl0', 'half_width', 'rds_snw')}
-        kw.setdefault('seed', seed)
-        self.run(c['n_photon'], c['wvl0'], c['half_width'], c['rds_snw'], write_output=write_output, **kw)
-        return (self.last_records, self.last_tally, self.last_table)
 
     # ---- n_scat / path-length histograms without records (post_processing.py:162-223) -------------------------------
     def histograms(self, n_photon, wvl0, half_width, rds_snw, n_scat_bins=200, path_length_bins=1000, theta_0=0.,
@@ -416,6 +480,30 @@ class MonteCarlo(object):
     def flatten_list(klass, l):
         """Concatenate per-rank record columns in rank order == photon order (monte_carlo3D.py:1845-1847)."""
         return {k: np.concatenate([part[k] for part in l]) for k in l[0]}
+
+
+def _tally_of_records(rec, n_rows, params):
+    """The tally block of one case from its record columns (same definition as the GPU's: counts by condition and
+    np.histogram / np.histogram2d of the reflected photons' angles over float64(angle))."""
+    n_theta, n_phi = int(params.n_theta_bins), max(1, int(params.n_phi_bins))
+    t = np.zeros((n_rows, engine.N_COND + n_theta * n_phi), np.uint64)
+    row = rec['wvl_row'].astype(np.int64)
+    np.add.at(t, (row, 0), 1)
+    np.add.at(t, (row, rec['condition'].astype(np.int64)), 1)
+    refl = rec['condition'] == 1
+    if n_theta > 0 and refl.any():
+        th = rec['theta_n'][refl].astype(np.float64)
+        r = row[refl]
+        if n_phi > 1:
+            ph = rec['phi_n'][refl].astype(np.float64)
+            for k in np.unique(r):
+                h, _, _ = np.histogram2d(th[r == k], ph[r == k], bins=(n_theta, n_phi), range=((0, np.pi / 2), (0, 2 * np.pi)))
+                t[k, engine.N_COND:] += h.astype(np.uint64).ravel()
+        else:
+            for k in np.unique(r):
+                h, _ = np.histogram(th[r == k], bins=n_theta, range=(0, np.pi / 2))
+                t[k, engine.N_COND:] += h.astype(np.uint64)
+    return t
 
 
 def test(n_photon=50000, wvl=0.5, half_width=0.085, rds_snw=100, **run_kwargs):

@@ -60,30 +60,42 @@ def test_known_answer_through_the_driver(run_dir, optics_root):
 
 
 def test_sweep_equals_case_by_case_runs(run_dir, optics_root, capsys):
-    # reference monte_carlo3D-run.py:60-96: wavelengths x grain sizes, one run() each; here batched over the slots
+    # reference monte_carlo3D-run.py:60-96: wavelengths x grain sizes, one run() each; here one launch per batch of cases
+    # (mc3d_run_sweep), case c being photons (c << 40) + j of the sweep's stream
+    grid = [(1.3, 0.085, 50, 15.), (1.3, 0.085, 100, 15.), (1.55, 0.130, 250, 0.), (1.55, 0.130, 500, 30.),
+            (0.9, 0.085, 1000, 60.), (2.2, 0.085, 100, 45.), (1.0, 0.085, 250, 15.), (1.3, 0.085, 1000, 15.),
+            (1.8, 0.26, 100, 15.), (1.3, 1e-12, 100, 15.), (1.3, 0.085, 100, 60.)]      # the last shares case 1's rows
     cases = [dict(n_photon=30000 + 1000 * k, wvl0=w, half_width=hw, rds_snw=r, theta_0=th, Lambertian_bottom=True,
-                  Lambertian_reflectance=0.5, seed=100 + k)
-             for k, (w, hw, r, th) in enumerate([(1.3, 0.085, 50, 15.), (1.3, 0.085, 100, 15.), (1.55, 0.130, 250, 0.),
-                                                  (1.55, 0.130, 500, 30.), (0.9, 0.085, 1000, 60.), (2.2, 0.085, 100, 45.),
-                                                  (1.0, 0.085, 250, 15.), (1.3, 0.085, 1000, 15.), (1.8, 0.26, 100, 15.),
-                                                  (1.3, 1e-12, 100, 15.)])]
+                  Lambertian_reflectance=0.5) for k, (w, hw, r, th) in enumerate(grid)]
     # an aspherical habit in the same sweep (needs HG=True): other table loader, other output directory
-    cases.insert(3, dict(n_photon=25000, wvl0=1.55, half_width=0.130, rds_snw=120, theta_0=30., seed=77,
+    cases.insert(3, dict(n_photon=25000, wvl0=1.55, half_width=0.130, rds_snw=120, theta_0=30.,
                          shape='solid hexagonal column', roughness='smooth'))
+    cases[6]['seed'] = 77                                    # a case with its own stream (starts a new batch)
     a = _model(run_dir, optics_root, tau_tot=8.0, HG=True)
     a.output_dir = str(run_dir / 'sweep')
-    paths = a.run_sweep(cases)
-    a.close()
+    paths = a.run_sweep(cases, seed=100, write_output='both')
+    assert a.last_seed == 100
     assert len(paths) == len(cases) and len(set(paths)) == len(cases)
     assert os.path.join('sweep', 'solid_column', 'Rough000') in paths[3] and os.path.join('sweep', 'sphere') in paths[4]
+    results = a.run_sweep(cases, seed=100, write_output=False)
+    a.close()
+    from monte_carlompi_b200 import output
     b = _model(run_dir, optics_root, tau_tot=8.0, HG=True)
     b.output_dir = str(run_dir / 'single')
-    for c, p in zip(cases, paths):
-        kw = {k: v for k, v in c.items() if k not in ('n_photon', 'wvl0', 'half_width', 'rds_snw')}
-        b.run(c['n_photon'], c['wvl0'], c['half_width'], c['rds_snw'], **kw)
+    for k, (c, p) in enumerate(zip(cases, paths)):
+        kw = {key: v for key, v in c.items() if key not in ('n_photon', 'wvl0', 'half_width', 'rds_snw')}
+        kw.setdefault('seed', 100)
+        b.run(c['n_photon'], c['wvl0'], c['half_width'], c['rds_snw'], first_photon_id=k << 40, **kw)
         q = capsys.readouterr().out.strip().splitlines()[-1]
         assert os.path.basename(p) == os.path.basename(q)
         assert open(p).read() == open(q).read()
+        rec, tally, table = results[k]
+        assert np.array_equal(tally, b.last_tally), k      # also for the two cases that share rows in one launch
+        assert np.array_equal(table, b.last_table)
+        for col in rec:
+            assert np.array_equal(rec[col], b.last_records[col]), (k, col)
+        z = np.load(output.sidecar_path(p))
+        assert np.array_equal(z['tally'], b.last_tally) and np.array_equal(z['n_scat'], rec['n_scat'])
     b.close()
 
 

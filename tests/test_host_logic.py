@@ -201,7 +201,7 @@ def _rdzv_worker(rank, root, q):
 
 def _allgather_worker(rank, root, q):
     par = parallelize.Parallel(100, environ={'RANK': str(rank), 'WORLD_SIZE': '2', 'LOCAL_RANK': str(rank)})
-    par._rdzv = parallelize.FileRendezvous(rank, 2, token='ag', root=root, timeout=30)   # what open() sets up
+    par.rendezvous(root=root, token='ag', timeout=30)                                       # what open() sets up
     ext = np.array([3. + rank, 40. - rank, 0.5 * (rank + 1), 9. + rank])                  # per-rank extrema
     parts = [np.frombuffer(b, np.float64) for b in par.allgather_bytes(ext.tobytes())]
     again = par.allgather_bytes(b'x%d' % rank)                                             # tags do not collide
@@ -226,6 +226,46 @@ def test_allgather_bytes_two_processes(tmp_path):
     assert got == [(0, want, [b'x0', b'x1']), (1, want, [b'x0', b'x1'])]
     assert not [d for d in os.listdir(str(tmp_path)) if d.startswith('mc3d_rdzv_')]       # rank 0 cleaned up after both left
     assert parallelize.Parallel(5, environ={}).allgather_bytes(b'solo') == [b'solo']
+
+
+def _two_instances_worker(rank, root, q):
+    """Two Parallel objects one after the other in the same job (the driver's multiple_wavelengths loop, or one
+    MonteCarlo per run): each gets its own rendezvous directory, so the second never reads the first one's NCCL id,
+    and closing the first -- at different times on the two ranks -- never removes a file of the second."""
+    import time
+    env = {'RANK': str(rank), 'WORLD_SIZE': '2', 'LOCAL_RANK': str(rank)}
+    got = []
+    for k in range(2):
+        par = parallelize.Parallel(1000 + k, environ=env)
+        rdzv = par.rendezvous(root=root, token='job', timeout=30)
+        if rank == 0:
+            time.sleep(0.3 * k)                                         # rank 1 runs ahead into instance 2
+            rdzv.put('nccl_id', b'id-of-instance-%d' % k)
+        got.append(rdzv.get('nccl_id'))
+        got.append(par.broadcast_seed(1234567890123456789 + k if rank == 0 else 7))
+        cols = {'condition': np.full(3 + rank, rank, np.uint8), 'theta_n': np.arange(3 + rank, dtype=np.float32) + 10 * rank}
+        ans = par.answer_and_reduce(cols, lambda parts: {c: np.concatenate([p[c] for p in parts]) for c in parts[0]})
+        got.append(None if ans is None else {c: v.tolist() for c, v in ans.items()})
+        if rank == 0:
+            time.sleep(0.3)                                             # rank 0 closes late
+        par.close()
+    q.put((rank, got))
+
+
+def test_two_parallel_instances_in_one_job(tmp_path):
+    shm_before = set(f for f in os.listdir('/dev/shm') if f.startswith('mc3d_'))
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_two_instances_worker, args=(r, str(tmp_path), q)) for r in range(2)]
+    [p.start() for p in ps]
+    got = dict(q.get(timeout=90) for _ in ps)
+    [p.join(30) for p in ps]
+    gathered = {'condition': [0, 0, 0, 1, 1, 1, 1], 'theta_n': [0., 1., 2., 10., 11., 12., 13.]}
+    for rank in (0, 1):
+        ans = gathered if rank == 0 else None
+        assert got[rank] == [b'id-of-instance-0', 1234567890123456789, ans, b'id-of-instance-1', 1234567890123456790, ans]
+    assert not [d for d in os.listdir(str(tmp_path)) if d.startswith('mc3d_rdzv_')]
+    assert set(f for f in os.listdir('/dev/shm') if f.startswith('mc3d_')) <= shm_before                                        # segments unlinked by their owners
 
 
 def test_file_rendezvous_two_processes(tmp_path):
