@@ -14,7 +14,7 @@ import numpy as np
 from monte_carloMPI import monte_carlo3D
 
 DEBUG = False
-LAMBERTIAN_SURFACE = False      # True would simulate a bare Lambertian surface (not built for B200)
+LAMBERTIAN_SURFACE = False      # True simulates a bare Lambertian surface instead of snow (monte_carlo3D.py:1228-1229)
 LAMBERTIAN_BOTTOM = True        # Lambertian lower boundary with the reflectance below
 LAMBERTIAN_REFLECTANCE = 0.5    # reflectance of the underlying surface beneath the snow
 

@@ -22,7 +22,9 @@ __device__ __forceinline__ int histogram_bin(double x, int n_bins, const double 
 // Block-level accumulation state: the shared-memory tally (when it fits), the optional column histograms behind it,
 // and per-thread running sums that finalize_flush() reduces.
 struct FinalizeBlock {
-    unsigned int *hist;              // [n_rows][stride] in shared memory when P.use_smem
+    unsigned int *hist;              // [win_rows][stride] in shared memory when P.use_smem: the tally rows [win_begin, +win_rows)
+    int win_begin, win_rows;         // use_smem == 1: the whole table; == 2 (sweep launches whose concatenated table does
+                                     // not fit): the rows of the case the block is working on, see finalize_window()
     unsigned int *xh;                // [n_scat_bins + path_bins] in shared memory when P.hist_smem
     unsigned int *block_ext;         // [4] shared: extrema of the block (minima complemented)
     unsigned long long *block_events;// shared
@@ -48,8 +50,10 @@ __device__ __forceinline__ void finalize_begin(const FinalizeParams &P, Finalize
     if (threadIdx.x == 0) *B.block_events = 0ull;
     B.n_phi = P.n_phi_bins > 1 ? P.n_phi_bins : 1;
     B.stride = N_COND + P.n_theta_bins * B.n_phi;
-    B.hist_len = P.n_rows * B.stride;
     B.tally = P.tally != nullptr;
+    B.win_begin = 0;
+    B.win_rows = P.use_smem == 2 ? 0 : P.n_rows;
+    B.hist_len = (P.use_smem == 2 ? P.win_rows : P.n_rows) * B.stride;
     B.xh_len = P.hist ? P.n_scat_bins + P.path_bins : 0;
     B.case_ev = nullptr;
     if (P.case_events && P.n_cases) {   // sweep launches: hist_base is 8-byte aligned
@@ -136,15 +140,58 @@ __device__ __forceinline__ void finalize_photon(const FinalizeParams &P, Finaliz
                 bin = pb >= 0 ? bin * B.n_phi + pb : -1;
             }
         }
-        if (P.use_smem) {   // [base + 0] (photons launched in this row) is formed from the condition counts at flush time
-            atomicAdd(&B.hist[base + cond], 1u);
-            if (bin >= 0) atomicAdd(&B.hist[base + N_COND + bin], 1u);
+        const uint32_t wrow = row - (uint32_t)B.win_begin;
+        if (P.use_smem && wrow < (uint32_t)B.win_rows) {   // [+ 0] (photons launched in this row) is formed from the condition counts at flush time
+            const int wbase = (int)wrow * B.stride;
+            atomicAdd(&B.hist[wbase + cond], 1u);
+            if (bin >= 0) atomicAdd(&B.hist[wbase + N_COND + bin], 1u);
         } else {
             atomicAdd(&P.tally[base], 1ull);
             atomicAdd(&P.tally[base + cond], 1ull);
             if (bin >= 0) atomicAdd(&P.tally[base + N_COND + bin], 1ull);
         }
     }
+}
+
+// The block's shared-memory tally rows -> the global tally: one 64-bit atomic per non-zero bin.  Every thread of the
+// block, after a __syncthreads() that ordered the photons' shared-memory atomics before it.
+template <int BLOCK>
+__device__ __forceinline__ void finalize_flush_tally(const FinalizeParams &P, const FinalizeBlock &B)
+{
+    const int len = B.win_rows * B.stride;
+    unsigned long long *dst = P.tally + (size_t)B.win_begin * B.stride;
+    for (int k = threadIdx.x; k < len; k += BLOCK) {
+        unsigned int v = B.hist[k];
+        if (k % B.stride == 0)
+            for (int c = 1; c < N_COND; ++c) v += B.hist[k + c];
+        if (v) atomicAdd(&dst[k], (unsigned long long)v);
+    }
+}
+
+// Sweep launches whose concatenated table is too large for a shared-memory tally (use_smem == 2) keep the rows of ONE
+// case there.  Photons are handed out in case order, so the 256 photons a block works on at a time almost always
+// belong to the case of the first of them, `base_pid`; the few of a neighbouring case at a boundary go straight to the
+// global tally.  Called by every thread of the block with the same (block-uniform) base_pid at the top of each
+// iteration of the photon loop; when the block has moved on to a case with other rows it flushes and re-targets.
+template <int BLOCK>
+__device__ __forceinline__ void finalize_window(const FinalizeParams &P, FinalizeBlock &B, uint32_t base_pid)
+{
+    if (P.use_smem != 2 || !B.tally) return;
+    uint32_t lo = 0u, hi = P.n_cases;
+    while (hi - lo > 1u) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (P.cases[mid].pid_first <= base_pid) lo = mid;
+        else hi = mid;
+    }
+    const int rb = (int)P.cases[lo].row_begin, nr = P.cases[lo].n_rows;
+    if (rb == B.win_begin && nr == B.win_rows) return;
+    __syncthreads();
+    finalize_flush_tally<BLOCK>(P, B);
+    __syncthreads();
+    B.win_begin = rb;
+    B.win_rows = nr <= P.win_rows ? nr : 0;
+    for (int k = threadIdx.x; k < B.win_rows * B.stride; k += BLOCK) B.hist[k] = 0u;
+    __syncthreads();
 }
 
 // Block reduction of the per-thread sums and flush of the shared-memory counts: one 64-bit global atomic per
@@ -171,14 +218,7 @@ __device__ __forceinline__ void finalize_flush(const FinalizeParams &P, Finalize
     __syncthreads();
     if (P.extrema && threadIdx.x < 4 && B.block_ext[threadIdx.x] != 0u) atomicMax(&P.extrema[threadIdx.x], B.block_ext[threadIdx.x]);
     if (threadIdx.x == 32 % BLOCK && *B.block_events) atomicAdd(P.n_events, *B.block_events);
-    if (B.tally && P.use_smem) {
-        for (int k = threadIdx.x; k < B.hist_len; k += BLOCK) {
-            unsigned int v = B.hist[k];
-            if (k % B.stride == 0)
-                for (int c = 1; c < N_COND; ++c) v += B.hist[k + c];
-            if (v) atomicAdd(&P.tally[k], (unsigned long long)v);
-        }
-    }
+    if (B.tally && P.use_smem) finalize_flush_tally<BLOCK>(P, B);
     if (B.case_ev) {
         for (int k = threadIdx.x; k < (int)P.n_cases; k += BLOCK) {
             const unsigned long long v = B.case_ev[k];
@@ -196,8 +236,13 @@ __device__ __forceinline__ void finalize_flush(const FinalizeParams &P, Finalize
 // Shared-memory budget of the tally / column histograms: sets use_smem / hist_smem in Q and returns the bytes.
 inline size_t finalize_plan_smem(FinalizeParams &Q, size_t tally_limit, size_t hist_limit)
 {
-    const size_t hist_bytes = (size_t)Q.n_rows * (N_COND + (size_t)Q.n_theta_bins * (Q.n_phi_bins > 1 ? Q.n_phi_bins : 1)) * sizeof(unsigned int);
+    const size_t row_bytes = (N_COND + (size_t)Q.n_theta_bins * (Q.n_phi_bins > 1 ? Q.n_phi_bins : 1)) * sizeof(unsigned int);
+    size_t hist_bytes = (size_t)Q.n_rows * row_bytes;
     Q.use_smem = (Q.tally != nullptr && hist_bytes <= tally_limit) ? 1 : 0;
+    if (Q.tally != nullptr && !Q.use_smem && Q.cases && Q.win_rows > 0 && (size_t)Q.win_rows * row_bytes <= tally_limit) {
+        Q.use_smem = 2;   // the rows of one case at a time (finalize_window)
+        hist_bytes = (size_t)Q.win_rows * row_bytes;
+    }
     const size_t xh_bytes = Q.hist ? ((size_t)Q.n_scat_bins + (size_t)Q.path_bins) * sizeof(unsigned int) : 0;
     Q.hist_smem = (xh_bytes > 0 && xh_bytes <= hist_limit) ? 1 : 0;
     const size_t case_bytes = (Q.case_events && Q.n_cases) ? (size_t)Q.n_cases * sizeof(unsigned long long) : 0;

@@ -30,7 +30,10 @@ __global__ void __launch_bounds__(BLOCK) finalize_kernel(const __grid_constant__
         for (int k = threadIdx.x; k < (int)P.n_cases; k += BLOCK) row_begin[k] = P.cases[k].row_begin;
     FinalizeBlock B;
     finalize_begin<BLOCK>(P, B, smem_u32 + ((P.n_rows + (SWEEP ? P.n_cases : 0u) + 1u) & ~1u), statics);   // 8-byte aligned
-    for (uint32_t p = blockIdx.x * BLOCK + threadIdx.x; p < P.n_photon; p += gridDim.x * BLOCK) {
+    for (uint32_t base = blockIdx.x * BLOCK; base < P.n_photon; base += gridDim.x * BLOCK) {
+        if (SWEEP) finalize_window<BLOCK>(P, B, base);
+        const uint32_t p = base + threadIdx.x;
+        if (p >= P.n_photon) continue;
         const RawResult *src = P.raw + p;
         const float4 a = *reinterpret_cast<const float4 *>(src);
         uint32_t n_scat, meta, lcase = 0u;

@@ -32,7 +32,10 @@ __global__ void __launch_bounds__(BLOCK) fused_kernel(const __grid_constant__ Wa
     FinalizeBlock B;
     finalize_begin<BLOCK>(F, B, reinterpret_cast<unsigned int *>(smem_raw + tables_bytes(P.n_rows, P.n_cases)), statics);
     const uint32_t rows_addr = shared_address(rows);
-    for (uint32_t pid = blockIdx.x * BLOCK + threadIdx.x; pid < P.n_photon; pid += gridDim.x * BLOCK) {
+    for (uint32_t base = blockIdx.x * BLOCK; base < P.n_photon; base += gridDim.x * BLOCK) {
+        if (SWEEP) finalize_window<BLOCK>(F, B, base);
+        const uint32_t pid = base + threadIdx.x;
+        if (pid >= P.n_photon) continue;
         Lane L;
         uint32_t row = 0;
         float dtau = 0.0f;

@@ -182,7 +182,8 @@ struct mc3d_ctx {
     int drain_give = -1;       // -1 = automatic (16 when other calls are in flight, else off); MC3D_DRAIN_GIVE overrides
     int drain_latency = -1;    // -1 = automatic (on for a call that runs alone); MC3D_DRAIN_LATENCY overrides
     int walk_path = MC3D_PATH_AUTO;   // mc3d_set_walk_path / MC3D_WALK_PATH
-    double fused_max_events = 12.0;   // automatic path: fused kernel when a photon is expected to end within this many events
+    double fused_max_events = 3.0;    // automatic path: fused kernel when a photon is expected to end within this many events
+                                      // (measured crossover with the persistent path: profiles/r02_fused_vs_persistent*.log)
     std::chrono::steady_clock::time_point t0[N_SLOTS];
     mc3d_stats pending_stats[N_SLOTS];
     bool hist_on = false;
@@ -350,7 +351,7 @@ static void apply_env(mc3d_ctx *ctx)
     const char *e = getenv("MC3D_DRAIN_GIVE");        // experiments only; results do not depend on it
     if (e && *e) ctx->drain_give = std::max(0, std::min(31, atoi(e)));
     e = getenv("MC3D_DRAIN_LATENCY");
-    if (e && *e) ctx->drain_latency = atoi(e) ? 1 : 0;
+    if (e && *e) ctx->drain_latency = std::max(0, std::min(2, atoi(e)));   // 1: group_latency, 2: group_pipelined
     e = getenv("MC3D_WALK_PATH");                     // same: "fused" | "persistent" | "auto"
     if (e && !strcmp(e, "fused")) ctx->walk_path = MC3D_PATH_FUSED;
     if (e && !strcmp(e, "persistent")) ctx->walk_path = MC3D_PATH_PERSISTENT;
@@ -698,7 +699,7 @@ static int run_job(mc3d_ctx *ctx, int slot_idx, const Job &J)
         bool others_busy = false;
         for (int s = 0; s < N_SLOTS; ++s) others_busy |= (s != slot_idx && ctx->devs[0].slot[s].busy);
         W.drain_give = ctx->drain_give >= 0 ? (uint32_t)ctx->drain_give : (others_busy ? 16u : 0u);
-        W.drain_latency = ctx->drain_latency >= 0 ? (uint32_t)ctx->drain_latency : (others_busy ? 0u : 1u);
+        W.drain_latency = ctx->drain_latency >= 0 ? (uint32_t)ctx->drain_latency : (others_busy ? 0u : 2u);
         lone = !others_busy;
     }
     double longest = 0.0;   // expected events per photon of the longest-lived case
@@ -928,6 +929,7 @@ static int run_job(mc3d_ctx *ctx, int slot_idx, const Job &J)
                 F.n_cases = Wc.n_cases;
                 F.case0 = Wc.case0;
                 F.case_events = d_case_ev;
+                for (int q = chunk_cases[c].first; q <= chunk_cases[c].second; ++q) F.win_rows = std::max(F.win_rows, J.cases[q].n_rows);
             }
             if (want_rec) {
                 records_layout(c_cnt, rec_off);

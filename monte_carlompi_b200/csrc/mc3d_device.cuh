@@ -116,7 +116,8 @@ struct WalkParams {
     uint32_t case0;         // sweep launches: global index of cases[0] (a photon's case index is id >> 40)
     uint32_t refill_threshold;
     uint32_t drain_give;    // drain phase: a warp with <= this many photons hands them to the block's pool (0 = off)
-    uint32_t drain_latency; // drain phase: latency-oriented groups (the launch runs alone: its tail is a dependent chain)
+    uint32_t drain_latency; // drain phase: latency-oriented groups (the launch runs alone: its tail is a dependent chain);
+                            // 1 = group_latency, 2 = group_pipelined (prepares the next group during the current one)
     uint32_t n_photon;      // photons in this launch (< 2^31)
     uint32_t pad;
     const DevRow *rows;     // [n_rows], global
@@ -135,7 +136,8 @@ struct FinalizeParams {
     int32_t n_rows;
     int32_t n_theta_bins;
     int32_t n_phi_bins;      // <= 1: zenith histogram only
-    int32_t use_smem;
+    int32_t use_smem;        // tally in shared memory: 0 no (global atomics), 1 the whole table, 2 one case's rows at a time
+    int32_t win_rows;        // sweep launches: the largest n_rows of the launch's cases (the window of use_smem == 2)
     // record columns (device), any may be null
     uint8_t *condition;
     int16_t *wvl_row;

@@ -43,6 +43,8 @@ def stage_reference():
                 'monte_carloMPI/config.ini'):
         shutil.copyfile(os.path.join(src, rel), os.path.join(STAGED_ROOT, rel))
     shutil.copyfile(os.path.join(src, 'monte_carloMPI', 'config.ini'), os.path.join(STAGED_ROOT, 'config.ini'))
+    # the reference's user script, for the test that runs it UNMODIFIED on top of the B200 package
+    shutil.copyfile(os.path.join(src, 'monte_carlo3D-run.py'), os.path.join(STAGED_ROOT, 'monte_carlo3D-run.py'))
     return True
 
 

@@ -1,11 +1,13 @@
 """The drop-in driver surface end to end on a GPU: MonteCarlo().run(...) -> output file, read back the way
 post_processing.py does."""
 import os
+import sys
 
 import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _model(run_dir, optics_root, kind='spectral', **kw):
@@ -57,6 +59,48 @@ def test_known_answer_through_the_driver(run_dir, optics_root):
     assert abs(trans - 0.66096) < 3.5 * np.sqrt(0.66 * 0.34 / n)
     assert mc.last_tally[:, 0].sum() == n
     mc.close()
+
+
+REFERENCE_RUN_SCRIPT_SHA256 = '02006f9a1e66265e10c5b0af5ae8d80f145d9f12d4ce69436047d49b6997c766'
+
+
+def test_unmodified_reference_run_script_drives_the_package(run_dir, optics_root):
+    """The reference's own user script (monte_carlo3D-run.py:4, 104-110: ``from monte_carloMPI import monte_carlo3D``,
+    ``MonteCarlo().run(...)``), byte for byte as staged from the reference by build() into the git-ignored
+    oracle/_ref/, run as a user would -- ``python monte_carlo3D-run.py`` in a directory with config.ini -- with this
+    repository first on the module path: the import resolves to the B200 package, the run happens on the GPU, and the
+    file it prints is the reference's (name, header, 10^4 rows, statistics of the driver-default golden case)."""
+    import hashlib
+    import subprocess
+    import golden_util as gu
+    script = os.path.join(ROOT, 'oracle', '_ref', 'reference', 'monte_carlo3D-run.py')
+    if not os.path.isfile(script):
+        pytest.skip('oracle/_ref/reference/monte_carlo3D-run.py not staged (build() stages it where /root/reference exists)')
+    assert hashlib.sha256(open(script, 'rb').read()).hexdigest() == REFERENCE_RUN_SCRIPT_SHA256
+    # a user keeps the script in the working directory, next to config.ini (python puts the script's own directory
+    # first on sys.path: left in oracle/_ref/reference it would import the reference package staged beside it)
+    import shutil
+    shutil.copyfile(script, str(run_dir / 'monte_carlo3D-run.py'))
+    script = str(run_dir / 'monte_carlo3D-run.py')
+    assert hashlib.sha256(open(script, 'rb').read()).hexdigest() == REFERENCE_RUN_SCRIPT_SHA256
+    env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get('PYTHONPATH', ''), CUDA_VISIBLE_DEVICES='0')
+    for k in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK'):
+        env.pop(k, None)
+    out = subprocess.run([sys.executable, script, '--optics_dir', optics_root['spectral']], cwd=str(run_dir), env=env,
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    path = out.stdout.strip().splitlines()[-1]                                # print(output_file), monte_carlo3D.py:1648
+    assert path == os.path.join('monte_carlo_results', 'sphere', '1.3_0.085_100.0_10000_14.999999999999998_HG.txt')
+    lines = open(str(run_dir / path)).read().splitlines()
+    assert lines[0] == 'condition wvn[um^-1] theta_n phi_n n_scat path_length[m], snow_depth[m]' and len(lines) == 10001
+    cond = np.array([int(l.split()[0]) for l in lines[1:]])
+    n_scat = np.array([int(l.split()[4]) for l in lines[1:]])
+    gold = gu.load_case('c1_full_10k')['golden']                           # the same script run on the reference
+    n = len(cond)
+    for c in (1, 4):
+        f, g = (cond == c).mean(), (gold['condition'] == c).mean()
+        assert abs(f - g) < 4 * np.sqrt(2 * g * (1 - g) / n) + 1e-3, (c, f, g)
+    assert abs(n_scat.mean() - gold['n_scat'].mean()) < 4 * np.sqrt(2) * gold['n_scat'].std() / np.sqrt(n)
 
 
 def test_sweep_equals_case_by_case_runs(run_dir, optics_root, capsys):

@@ -122,19 +122,25 @@ def test_lambertian_surface_mode():
 
 
 # ---------------------------------------------------------------------------------------------- 2. vs the reference
-def _stats_file():
-    return os.path.join(gu.GOLDEN_DIR, 'stats_c2_reference.npz')
+def _stats_file(name='c2'):
+    return os.path.join(gu.GOLDEN_DIR, 'stats_%s_reference.npz' % name)
 
 
-@pytest.mark.skipif(not os.path.isfile(_stats_file()), reason='reference statistics fixture not generated')
-def test_outcomes_and_brf_within_3_sigma_of_reference(optics_root):
+# c2: BASELINE.json configs[1] (semi-infinite).  slab_lb: tau_tot = 3 over a Lambertian bottom R = 0.5 (all of
+# conditions 1-4; bottom reflections re-enter the walk).  impurity: tau_tot = 3 with 1e-5 black carbon (species draw,
+# condition 5).  Each is 10^6 photons of the unmodified reference (oracle/make_golden_stats.py).
+@pytest.mark.parametrize('name', ['c2', 'slab_lb', 'impurity'])
+def test_outcomes_and_brf_within_3_sigma_of_reference(optics_root, name):
     from monte_carlompi_b200 import ssp
-    z = np.load(_stats_file())
+    if not os.path.isfile(_stats_file(name)):
+        pytest.skip('reference statistics fixture not generated')
+    z = np.load(_stats_file(name))
     cfg = ast.literal_eval(str(z['config']))
     n_ref = cfg['n_photon']
     scale = cfg['half_width'] / 2.355
     k_lo, k_hi = ssp.wavelength_grid(cfg['wvl0'], scale)
-    rows = ssp.build_table(optics_root[cfg['fixture']], 'mie_sot_ChC90_dns_1317.nc', cfg['rds_snw'], k_lo, k_hi, 0.0)
+    rows = ssp.build_table(optics_root[cfg['fixture']], 'mie_sot_ChC90_dns_1317.nc', cfg['rds_snw'], k_lo, k_hi,
+                           cfg.get('imp_cnc', 0.0))
     P = engine.make_params(np.pi * cfg['theta_0'] / 180., cfg['tau_tot'], 300., cfg['Lambertian_reflectance'], cfg['wvl0'],
                            scale, k_lo, lambert_bottom=cfg['Lambertian_bottom'], n_theta_bins=cfg['n_theta_bins'])
     n_gpu = 8000000
@@ -152,6 +158,10 @@ def test_outcomes_and_brf_within_3_sigma_of_reference(optics_root):
     # outcome fractions (reflected, diffuse / direct transmitted, absorbed)
     for cond in (1, 2, 3, 4, 5):
         check(tally[:, cond].sum(), z['counts'][:, cond].sum(), 'condition %d' % cond)
+    if name == 'slab_lb':
+        assert min(z['counts'][:, c].sum() for c in (1, 2, 3, 4)) > 10000       # the fixture exercises every outcome
+    if name == 'impurity':
+        assert z['counts'][:, 5].sum() > 10000 and tally[:, 5].sum() > 10000
     # wavelength distribution of the drawn photons, per 10 nm bin (Box-Muller on Philox vs numpy's legacy normal)
     kr = int(z['k_first'])
     zs_w = [check(tally[kr - k_lo + j, 0], z['counts'][j, 0], 'wavelength row %d' % j, z_max=4.5)
@@ -172,16 +182,19 @@ def test_outcomes_and_brf_within_3_sigma_of_reference(optics_root):
     assert abs(mean_gpu - mean_ref) < 3.5 * np.sqrt(var_ref * (1.0 / n_ref + 1.0 / n_gpu))
 
 
-@pytest.mark.skipif(not os.path.isfile(_stats_file()), reason='reference statistics fixture not generated')
-def test_path_length_statistics_match_reference(optics_root):
+@pytest.mark.parametrize('name', ['c2', 'slab_lb', 'impurity'])
+def test_path_length_statistics_match_reference(optics_root, name):
     # mean photon path length inside the slab (all photons, and reflected ones) against the reference at 10^6 photons
     from monte_carlompi_b200 import ssp
-    z = np.load(_stats_file())
+    if not os.path.isfile(_stats_file(name)):
+        pytest.skip('reference statistics fixture not generated')
+    z = np.load(_stats_file(name))
     cfg = ast.literal_eval(str(z['config']))
     n_ref = cfg['n_photon']
     scale = cfg['half_width'] / 2.355
     k_lo, k_hi = ssp.wavelength_grid(cfg['wvl0'], scale)
-    rows = ssp.build_table(optics_root[cfg['fixture']], 'mie_sot_ChC90_dns_1317.nc', cfg['rds_snw'], k_lo, k_hi, 0.0)
+    rows = ssp.build_table(optics_root[cfg['fixture']], 'mie_sot_ChC90_dns_1317.nc', cfg['rds_snw'], k_lo, k_hi,
+                           cfg.get('imp_cnc', 0.0))
     P = engine.make_params(np.pi * cfg['theta_0'] / 180., cfg['tau_tot'], 300., cfg['Lambertian_reflectance'], cfg['wvl0'],
                            scale, k_lo, lambert_bottom=cfg['Lambertian_bottom'], n_theta_bins=cfg['n_theta_bins'])
     n = 4000000

@@ -148,6 +148,36 @@ def test_sweep_across_launch_chunks():
     assert np.array_equal(tally, expect)
 
 
+@pytest.mark.parametrize('path,wvl0', [('fused', 2.1), ('persistent', 1.5), ('auto', 1.7)])
+def test_sweep_with_a_table_too_large_for_a_shared_memory_tally(path, wvl0):
+    """Five grain sizes x five zenith angles of one wavelength (one iteration of the reference driver's loops,
+    monte_carlo3D-run.py:60-96): 265 rows x 145 tally words do not fit in shared memory, so the blocks keep the rows of
+    the case they are working on there and re-target as they move through the cases (finalize_window)."""
+    k0 = int(round(wvl0 * 100)) - 26
+    tables = [gpu_util.fixture_table('spectral', r, k0, k0 + 52) for r in (50, 100, 250, 500, 1000)]
+    table = np.concatenate(tables)
+    cases = []
+    for j in range(5):
+        for th in (0., 15., 30., 45., 60.):
+            pe = engine.make_params(np.pi * th / 180., 1e6, 300., .5, wvl0, SIGMA, k0, lambert_bottom=True, n_theta_bins=137)
+            cases.append((pe, 53 * j, 53, 20000 + 777 * len(cases)))
+    ctx = gpu_util.context()
+    try:
+        ctx.set_walk_path(path)
+        per_case, tally, events, st = ctx.run_sweep(cases, table, 11)
+    finally:
+        ctx.set_walk_path('auto')
+    expect = np.zeros_like(tally)
+    for c, (pe, rb, nr, n) in enumerate(cases):
+        rec, t, s = ctx.run(pe, table[rb:rb + nr], 11, c << engine.SWEEP_ID_SHIFT, n)
+        for col in rec:
+            assert np.array_equal(per_case[c][col], rec[col]), (c, col)
+        expect[rb:rb + nr] += t
+        assert int(events[c]) == int(s['n_events']), c
+    assert np.array_equal(tally, expect)
+    assert tally[:, 0].sum() == sum(c[3] for c in cases)
+
+
 def test_sweep_rejects_bad_arguments():
     table, cases, _ = _cases()
     ctx = gpu_util.context()
