@@ -53,7 +53,7 @@ __device__ __forceinline__ void finalize_begin(const FinalizeParams &P, Finalize
     B.tally = P.tally != nullptr;
     B.win_begin = 0;
     B.win_rows = P.use_smem == 2 ? 0 : P.n_rows;
-    B.hist_len = (P.use_smem == 2 ? P.win_rows : P.n_rows) * B.stride;
+    B.hist_len = P.use_smem == 3 ? P.n_rows * N_COND : (P.use_smem == 2 ? P.win_rows : P.n_rows) * B.stride;
     B.xh_len = P.hist ? P.n_scat_bins + P.path_bins : 0;
     B.case_ev = nullptr;
     if (P.case_events && P.n_cases) {   // sweep launches: hist_base is 8-byte aligned
@@ -141,7 +141,10 @@ __device__ __forceinline__ void finalize_photon(const FinalizeParams &P, Finaliz
             }
         }
         const uint32_t wrow = row - (uint32_t)B.win_begin;
-        if (P.use_smem && wrow < (uint32_t)B.win_rows) {   // [+ 0] (photons launched in this row) is formed from the condition counts at flush time
+        if (P.use_smem == 3) {   // outcome counts of every row in shared memory, BRF bins (reflected photons only) global
+            atomicAdd(&B.hist[(int)row * N_COND + cond], 1u);
+            if (bin >= 0) atomicAdd(&P.tally[base + N_COND + bin], 1ull);
+        } else if (P.use_smem && wrow < (uint32_t)B.win_rows) {   // [+ 0] (photons launched in this row) is formed from the condition counts at flush time
             const int wbase = (int)wrow * B.stride;
             atomicAdd(&B.hist[wbase + cond], 1u);
             if (bin >= 0) atomicAdd(&B.hist[wbase + N_COND + bin], 1u);
@@ -158,6 +161,15 @@ __device__ __forceinline__ void finalize_photon(const FinalizeParams &P, Finaliz
 template <int BLOCK>
 __device__ __forceinline__ void finalize_flush_tally(const FinalizeParams &P, const FinalizeBlock &B)
 {
+    if (P.use_smem == 3) {
+        for (int k = threadIdx.x; k < P.n_rows * N_COND; k += BLOCK) {
+            unsigned int v = B.hist[k];
+            if (k % N_COND == 0)
+                for (int c = 1; c < N_COND; ++c) v += B.hist[k + c];
+            if (v) atomicAdd(&P.tally[(size_t)(k / N_COND) * B.stride + k % N_COND], (unsigned long long)v);
+        }
+        return;
+    }
     const int len = B.win_rows * B.stride;
     unsigned long long *dst = P.tally + (size_t)B.win_begin * B.stride;
     for (int k = threadIdx.x; k < len; k += BLOCK) {
@@ -234,14 +246,20 @@ __device__ __forceinline__ void finalize_flush(const FinalizeParams &P, Finalize
 }
 
 // Shared-memory budget of the tally / column histograms: sets use_smem / hist_smem in Q and returns the bytes.
-inline size_t finalize_plan_smem(FinalizeParams &Q, size_t tally_limit, size_t hist_limit)
+// `windowed`: the kernel's blocks move through the photons in step (finalize_window is usable); otherwise a table that
+// does not fit keeps only its outcome counts in shared memory (use_smem == 3).
+inline size_t finalize_plan_smem(FinalizeParams &Q, size_t tally_limit, size_t hist_limit, bool windowed = true)
 {
     const size_t row_bytes = (N_COND + (size_t)Q.n_theta_bins * (Q.n_phi_bins > 1 ? Q.n_phi_bins : 1)) * sizeof(unsigned int);
     size_t hist_bytes = (size_t)Q.n_rows * row_bytes;
     Q.use_smem = (Q.tally != nullptr && hist_bytes <= tally_limit) ? 1 : 0;
-    if (Q.tally != nullptr && !Q.use_smem && Q.cases && Q.win_rows > 0 && (size_t)Q.win_rows * row_bytes <= tally_limit) {
+    if (Q.tally != nullptr && !Q.use_smem && windowed && Q.cases && Q.win_rows > 0 && (size_t)Q.win_rows * row_bytes <= tally_limit) {
         Q.use_smem = 2;   // the rows of one case at a time (finalize_window)
         hist_bytes = (size_t)Q.win_rows * row_bytes;
+    }
+    if (Q.tally != nullptr && !Q.use_smem && !windowed && (size_t)Q.n_rows * N_COND * sizeof(unsigned int) <= tally_limit) {
+        Q.use_smem = 3;
+        hist_bytes = (size_t)Q.n_rows * N_COND * sizeof(unsigned int);
     }
     const size_t xh_bytes = Q.hist ? ((size_t)Q.n_scat_bins + (size_t)Q.path_bins) * sizeof(unsigned int) : 0;
     Q.hist_smem = (xh_bytes > 0 && xh_bytes <= hist_limit) ? 1 : 0;

@@ -27,10 +27,15 @@ __global__ void __launch_bounds__(BLOCK) init_kernel(const __grid_constant__ Wal
     stage_tables(P, smem_raw, BLOCK);
     __syncthreads();
     const uint32_t rows_addr = shared_address(rows);
-    const uint32_t lane = threadIdx.x & 31u;
-    // whole warps iterate together so that the ballot below is always executed by all 32 lanes
-    for (uint32_t base = (blockIdx.x * BLOCK + (threadIdx.x & ~31u)); base < P.n_photon; base += gridDim.x * BLOCK) {
-        const uint32_t pid = base + lane;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    // One append per BLOCK and iteration (256 photons), not per warp: the list length is a single address, and returning
+    // atomics on one address serialise in L2 at ~1 per ns -- with one per warp that alone took 0.27 ms per 10^7
+    // photons (profiles/r02_persistent_short_walk_launches.csv), several times the kernel's arithmetic.
+    __shared__ uint32_t warp_count[BLOCK / 32];
+    __shared__ uint32_t block_base;
+    // whole blocks iterate together (uniform trip count: the barriers below are executed by every thread)
+    for (uint32_t base = blockIdx.x * BLOCK; base < P.n_photon; base += gridDim.x * BLOCK) {
+        const uint32_t pid = base + threadIdx.x;
         bool survive = false;
         uint32_t redo = 0u;
         float dtau = 0.0f;
@@ -50,14 +55,23 @@ __global__ void __launch_bounds__(BLOCK) init_kernel(const __grid_constant__ Wal
             else store_raw(P, pid, L.ux, L.uy, L.uz, __fadd_rn(L.path_hi, L.path_lo), L.i - 1u, cond, row, lcase);
         }
         const uint32_t m = __ballot_sync(0xffffffffu, survive);
-        uint32_t slot0 = 0;
-        if (lane == 0 && m) slot0 = atomicAdd(P.n_fresh, (uint32_t)__popc(m));
-        slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+        if (lane == 0) warp_count[warp] = (uint32_t)__popc(m);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t total = 0;
+#pragma unroll
+            for (int w = 0; w < BLOCK / 32; ++w) total += warp_count[w];
+            block_base = total ? atomicAdd(P.n_fresh, total) : 0u;
+        }
+        __syncthreads();
         if (survive) {
+            uint32_t at = block_base + __popc(m & ((1u << lane) - 1u));
+            for (uint32_t w = 0; w < warp; ++w) at += warp_count[w];
             Fresh f;
             f.pid = pid; f.row = row | (lcase << 12); f.dtau = dtau; f.redo = redo;
-            *reinterpret_cast<uint4 *>(P.fresh + slot0 + __popc(m & ((1u << lane) - 1u))) = *reinterpret_cast<uint4 *>(&f);
+            *reinterpret_cast<uint4 *>(P.fresh + at) = *reinterpret_cast<uint4 *>(&f);
         }
+        __syncthreads();   // warp_count / block_base are rewritten by the next iteration
     }
 }
 

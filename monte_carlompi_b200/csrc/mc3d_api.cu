@@ -182,7 +182,7 @@ struct mc3d_ctx {
     int drain_give = -1;       // -1 = automatic (16 when other calls are in flight, else off); MC3D_DRAIN_GIVE overrides
     int drain_latency = -1;    // -1 = automatic (on for a call that runs alone); MC3D_DRAIN_LATENCY overrides
     int walk_path = MC3D_PATH_AUTO;   // mc3d_set_walk_path / MC3D_WALK_PATH
-    double fused_max_events = 3.0;    // automatic path: fused kernel when a photon is expected to end within this many events
+    double fused_max_events = 2.5;    // automatic path: fused kernel when a photon is expected to end within this many events
                                       // (measured crossover with the persistent path: profiles/r02_fused_vs_persistent*.log)
     std::chrono::steady_clock::time_point t0[N_SLOTS];
     mc3d_stats pending_stats[N_SLOTS];
@@ -705,6 +705,7 @@ static int run_job(mc3d_ctx *ctx, int slot_idx, const Job &J)
     double longest = 0.0;   // expected events per photon of the longest-lived case
     for (const HostCase &c : J.cases) longest = std::max(longest, expected_events(&c.params, J.table + c.row_begin, c.n_rows));
     const bool fused = ctx->walk_path == MC3D_PATH_FUSED || (ctx->walk_path == MC3D_PATH_AUTO && longest <= ctx->fused_max_events);
+    W.claim = longest <= 4.0 ? 96u : (longest <= 16.0 ? 64u : 32u);   // fewer, larger claims of the fresh list when walks are short
 
     ctx->done_hist[slot_idx] = ctx->hist_on;
     ctx->done_spec[slot_idx] = ctx->hist_spec;

@@ -119,7 +119,7 @@ struct WalkParams {
     uint32_t drain_latency; // drain phase: latency-oriented groups (the launch runs alone: its tail is a dependent chain);
                             // 1 = group_latency, 2 = group_pipelined (prepares the next group during the current one)
     uint32_t n_photon;      // photons in this launch (< 2^31)
-    uint32_t pad;
+    uint32_t claim;         // walk kernel: entries of `fresh` a warp claims per atomicAdd (32, 64 or 96)
     const DevRow *rows;     // [n_rows], global
     const DevCase *cases;   // [n_cases], global (sweep launches)
     uint32_t *counter;      // walk kernel: next unclaimed entry of `fresh`
@@ -136,7 +136,8 @@ struct FinalizeParams {
     int32_t n_rows;
     int32_t n_theta_bins;
     int32_t n_phi_bins;      // <= 1: zenith histogram only
-    int32_t use_smem;        // tally in shared memory: 0 no (global atomics), 1 the whole table, 2 one case's rows at a time
+    int32_t use_smem;        // tally in shared memory: 0 no (global atomics), 1 the whole table, 2 one case's rows at a time,
+                             // 3 the outcome counts of every row (BRF bins global)
     int32_t win_rows;        // sweep launches: the largest n_rows of the launch's cases (the window of use_smem == 2)
     // record columns (device), any may be null
     uint8_t *condition;

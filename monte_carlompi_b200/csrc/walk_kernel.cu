@@ -14,7 +14,7 @@
 //   * when `refill_threshold` lanes of a warp are waiting, the warp takes one uniform branch: the waiting lanes
 //     are resolved together (the reference's termination chain in its order; finished photons store one 32-byte
 //     raw record) and the empty ones pop a fresh photon from a per-warp shared-memory ring.  The ring is refilled
-//     32 photons per atomicAdd (warp-aggregated by construction) with one coalesced 512-byte load from the
+//     32 (short walks: 96) photons per atomicAdd (warp-aggregated by construction) with coalesced 512-byte loads from the
 //     `fresh` list the init kernel wrote (wavelength draw, SSP row and the deflection-free first event,
 //     monte_carlo3D.py:1232-1237, happen there).  So the divergent part of a refill is a handful of
 //     shared-memory loads, and walk-length divergence is bounded by the threshold instead of by the longest
@@ -41,7 +41,7 @@ __device__ __forceinline__ unsigned long long now_ns() { unsigned long long t; a
 #define TIMELINE(slot) do { } while (0)
 #endif
 
-constexpr int RING = 64;  // entries per warp; a refill adds at most 32 to fewer than 32 leftovers
+constexpr int RING = 128;  // entries per warp; a refill adds at most P.claim <= 96 to fewer than 32 leftovers
 
 // Fresh photons staged for the lanes of one warp.
 struct WarpRing {
@@ -102,6 +102,9 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) walk_kernel(const __grid_co
     uint32_t ring_head = 0, ring_tail = 0;   // warp-uniform, free-running
     const uint32_t threshold = max(1u, min(32u, P.refill_threshold));
     const uint32_t n_fresh = *P.n_fresh;     // complete: the init kernel ran before this launch
+    // photons claimed per atomicAdd: 32, or 64 / 96 for short walks, where one claim per 32 photons would run into the
+    // rate at which L2 serialises returning atomics on one address (~1 per ns)
+    const uint32_t claim = max(32u, min(96u, P.claim));
 
     Lane L;
     L.z = 0.f; L.ux = 0.f; L.uy = 0.f; L.uz = -1.f; L.path_lo = 0.f; L.path_hi = 0.f;
@@ -121,12 +124,12 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) walk_kernel(const __grid_co
             bool exhausted = false;
             while ((ring_tail - ring_head) < need) {
                 uint32_t base = 0;
-                if (lane == 0) base = atomicAdd(P.counter, 32u);
+                if (lane == 0) base = atomicAdd(P.counter, claim);
                 base = __shfl_sync(0xffffffffu, base, 0);
                 if (base >= n_fresh) { exhausted = true; break; }
-                const uint32_t got = min(32u, n_fresh - base);
-                if (lane < got)
-                    Q.entry[(ring_tail + lane) & (RING - 1)] = *reinterpret_cast<const uint4 *>(P.fresh + base + lane);
+                const uint32_t got = min(claim, n_fresh - base);
+                for (uint32_t k = lane; k < got; k += 32u)
+                    Q.entry[(ring_tail + k) & (RING - 1)] = *reinterpret_cast<const uint4 *>(P.fresh + base + k);
                 ring_tail += got;
                 __syncwarp();
             }
@@ -178,7 +181,11 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) walk_kernel(const __grid_co
     uint32_t peek = 0u;
     // the launch runs alone: groups software-pipelined across the photon's own stream (group_pipelined; impurity runs
     // draw the species between events and keep group_latency)
+#ifdef MC3D_NO_PIPELINED
+    const bool pipelined = false;
+#else
     const bool pipelined = !IMP && P.drain_latency >= 2u;
+#endif
     Lookahead K;
     K.e0.ct = K.e0.st2 = K.e0.cp = K.e0.sp = K.e0.dtau = 0.0f; K.e0.key = 0u;
     K.e1 = K.e0; K.bz = 0u; K.bw = 0u;
