@@ -351,7 +351,7 @@ static void apply_env(mc3d_ctx *ctx)
     const char *e = getenv("MC3D_DRAIN_GIVE");        // experiments only; results do not depend on it
     if (e && *e) ctx->drain_give = std::max(0, std::min(31, atoi(e)));
     e = getenv("MC3D_DRAIN_LATENCY");
-    if (e && *e) ctx->drain_latency = std::max(0, std::min(2, atoi(e)));   // 1: group_latency, 2: group_pipelined
+    if (e && *e) ctx->drain_latency = atoi(e) ? 1 : 0;
     e = getenv("MC3D_WALK_PATH");                     // same: "fused" | "persistent" | "auto"
     if (e && !strcmp(e, "fused")) ctx->walk_path = MC3D_PATH_FUSED;
     if (e && !strcmp(e, "persistent")) ctx->walk_path = MC3D_PATH_PERSISTENT;
@@ -699,7 +699,7 @@ static int run_job(mc3d_ctx *ctx, int slot_idx, const Job &J)
         bool others_busy = false;
         for (int s = 0; s < N_SLOTS; ++s) others_busy |= (s != slot_idx && ctx->devs[0].slot[s].busy);
         W.drain_give = ctx->drain_give >= 0 ? (uint32_t)ctx->drain_give : (others_busy ? 16u : 0u);
-        W.drain_latency = ctx->drain_latency >= 0 ? (uint32_t)ctx->drain_latency : (others_busy ? 0u : 2u);
+        W.drain_latency = ctx->drain_latency >= 0 ? (uint32_t)ctx->drain_latency : (others_busy ? 0u : 1u);
         lone = !others_busy;
     }
     double longest = 0.0;   // expected events per photon of the longest-lived case

@@ -116,8 +116,7 @@ struct WalkParams {
     uint32_t case0;         // sweep launches: global index of cases[0] (a photon's case index is id >> 40)
     uint32_t refill_threshold;
     uint32_t drain_give;    // drain phase: a warp with <= this many photons hands them to the block's pool (0 = off)
-    uint32_t drain_latency; // drain phase: latency-oriented groups (the launch runs alone: its tail is a dependent chain);
-                            // 1 = group_latency, 2 = group_pipelined (prepares the next group during the current one)
+    uint32_t drain_latency; // drain phase: latency-oriented groups (the launch runs alone: its tail is a dependent chain)
     uint32_t n_photon;      // photons in this launch (< 2^31)
     uint32_t claim;         // walk kernel: entries of `fresh` a warp claims per atomicAdd (32, 64 or 96)
     const DevRow *rows;     // [n_rows], global

@@ -335,60 +335,6 @@ __device__ __forceinline__ bool group_latency(const WalkParams &P, const DevRow 
     return go;
 }
 
-// The latency-oriented group, software-pipelined across groups.  A photon's next group is always the one after the
-// current group -- whether the current one runs to its end or is cut short by an event that needs attention (see the
-// random-number layout) -- so everything of group G+1 that does not depend on the photon's direction (its Philox
-// blocks, deflection, azimuth, free path) can be computed while the rotations of group G, a dependent chain, are
-// still in flight.  A lane carries the first half of its next group (Lookahead: events 0 and 1 prepared, plus the two
-// words of block b that belong to event 2); each call finishes the second half of the current group, prepares the
-// first half of the next, and applies the four events.  Same values, same stream as group() / group_latency().
-struct Lookahead {
-    Prepared e0, e1;
-    uint32_t bz, bw;
-};
-
-template <bool SWEEP>
-__device__ __forceinline__ Lookahead prime_lookahead(const WalkParams &P, const Lane &L)
-{
-    const HotRow H = load_hot_row<SWEEP>(P, L.row_addr);
-    const uint32_t phi = lane_phi<SWEEP>(P, L);
-    const uint4 a = philox_walk(L.blk, phi, L.pk, P.rk);
-    const uint4 b = philox_walk(L.blk + 1u, phi, L.pk, P.rk);
-    Lookahead K;
-    K.e0 = prepare_event(H, a.x, a.y, a.z);
-    K.e1 = prepare_event(H, a.w, b.x, b.y);
-    K.bz = b.z; K.bw = b.w;
-    return K;
-}
-
-template <bool SWEEP>
-__device__ __forceinline__ bool group_pipelined(const WalkParams &P, Lane &L, Lookahead &K)
-{
-    const HotRow H = load_hot_row<SWEEP>(P, L.row_addr);
-    const uint32_t phi = lane_phi<SWEEP>(P, L);
-    const uint32_t n = L.blk;
-    L.blk = n + GROUP_BLOCKS;
-    const uint4 c = philox_walk(n + 2u, phi, L.pk, P.rk);
-    const uint4 a2 = philox_walk(n + 3u, phi, L.pk, P.rk);
-    const uint4 b2 = philox_walk(n + 4u, phi, L.pk, P.rk);
-    const Prepared ev[4] = {K.e0, K.e1, prepare_event(H, K.bz, K.bw, c.x), prepare_event(H, c.y, c.z, c.w)};
-    K.e0 = prepare_event(H, a2.x, a2.y, a2.z);
-    K.e1 = prepare_event(H, a2.w, b2.x, b2.y);
-    K.bz = b2.z; K.bw = b2.w;
-    bool go = true;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        Lane N = L;
-        N.i += 1u;
-        apply_event(N, ev[k]);
-        const bool att = needs_attention(H.neg_tau, N, H.t_hot);
-        L.z = go ? N.z : L.z; L.ux = go ? N.ux : L.ux; L.uy = go ? N.uy : L.uy; L.uz = go ? N.uz : L.uz;
-        L.path_lo = go ? N.path_lo : L.path_lo; L.key = go ? N.key : L.key; L.i = go ? N.i : L.i;
-        go = go && !att;
-    }
-    return go;
-}
-
 // ---- tables in shared memory: the SSP rows, then (sweep launches) the cases ------------------------------------------
 __host__ __device__ __forceinline__ size_t tables_bytes(int n_rows, uint32_t n_cases)
 {

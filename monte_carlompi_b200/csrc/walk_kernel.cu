@@ -179,17 +179,6 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) walk_kernel(const __grid_co
     // Unlocked peek at the pool: (count << 8) | draining, lane 0's view, so every branch on it is warp-uniform.
     // Refreshed once per iteration, one event stale; every decision is re-made under the lock.
     uint32_t peek = 0u;
-    // the launch runs alone: groups software-pipelined across the photon's own stream (group_pipelined; impurity runs
-    // draw the species between events and keep group_latency)
-#ifdef MC3D_NO_PIPELINED
-    const bool pipelined = false;
-#else
-    const bool pipelined = !IMP && P.drain_latency >= 2u;
-#endif
-    Lookahead K;
-    K.e0.ct = K.e0.st2 = K.e0.cp = K.e0.sp = K.e0.dtau = 0.0f; K.e0.key = 0u;
-    K.e1 = K.e0; K.bz = 0u; K.bw = 0u;
-    if (pipelined && L.i != 0u) K = prime_lookahead<SWEEP>(P, L);
     for (;;) {
         if (!alive && L.i != 0u) alive = resolve_lane<IMP, SWEEP>(P, cases, rows, rows_addr, L);
         const uint32_t alive_mask = __ballot_sync(0xffffffffu, alive);
@@ -242,16 +231,12 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) walk_kernel(const __grid_co
                 if (taken) {   // outside the lock: rebuild the Philox state of the photon just taken over
                     L.pk = philox_walk_constants(L.plo, P.rk);
                     alive = true;
-                    if (pipelined) K = prime_lookahead<SWEEP>(P, L);
                 }
             }
         }
         if (give_max != 0u)
             peek = __shfl_sync(0xffffffffu, lane == 0 ? (pool_get(&D.count) << 8) | min(pool_get(&D.draining), 255u) : 0u, 0);
-        if (alive) {
-            if (pipelined) alive = group_pipelined<SWEEP>(P, L, K);
-            else alive = P.drain_latency ? group_latency<IMP, SWEEP>(P, rows, rows_addr, L) : group<IMP, true, SWEEP>(P, rows, rows_addr, L);
-        }
+        if (alive) alive = P.drain_latency ? group_latency<IMP, SWEEP>(P, rows, rows_addr, L) : group<IMP, true, SWEEP>(P, rows, rows_addr, L);
     }
 }
 
