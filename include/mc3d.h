@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define MC3D_ABI_VERSION 3
+#define MC3D_ABI_VERSION 4
 
 /* error codes */
 #define MC3D_OK 0
@@ -286,6 +286,15 @@ int mc3d_set_launch(mc3d_ctx *ctx, int blocks_per_sm, int block_threads, int ref
 #define MC3D_PATH_FUSED 1
 #define MC3D_PATH_PERSISTENT 2
 int mc3d_set_walk_path(mc3d_ctx *ctx, int path);
+
+/* How a persistent-path call ends.  When the last photon has been handed out every lane still carries one, and the
+ * call ends with its longest walk (the `while` loop of one photon, monte_carlo3D.py:1212-1466, is a sequential chain).
+ * mode 1: the walk kernel hands those photons to a tail kernel (dense warps; once a warp is down to four photons its
+ * idle lanes prepare the photons' next events, which halves the time per event of a lone walk).  mode 0: the walk
+ * kernel drains by itself, and draining warps consolidate when other calls are in flight.  mode -1 (default): 1 for a
+ * call that starts with no other call in flight on the context, else 0.  A performance choice only: bit-identical
+ * results either way. */
+int mc3d_set_tail_kernel(mc3d_ctx *ctx, int mode);
 
 /* Input caching (default on): a call whose SSP table, bin edges and histogram edges equal what its slot uploaded
  * last time skips the host-to-device copy (a few KB).  enabled = 0 makes every call upload its inputs again. */

@@ -32,6 +32,7 @@ namespace mc3d {
 cudaError_t launch_walk(const WalkParams &P, bool impurity, int block_threads, int blocks_per_sm, int grid,
                         cudaStream_t stream, int *occupancy);
 cudaError_t launch_init(const WalkParams &P, bool impurity, int sm_count, cudaStream_t stream);
+cudaError_t launch_tail(const WalkParams &P, bool impurity, int lanes, cudaStream_t stream);
 cudaError_t launch_finalize(const FinalizeParams &P, int sm_count, cudaStream_t stream);
 cudaError_t launch_fused(const WalkParams &P, const FinalizeParams &F, bool impurity, int sm_count, cudaStream_t stream);
 cudaError_t launch_replay(const ReplayParams &P, cudaStream_t stream);
@@ -143,12 +144,13 @@ struct Slot {
     size_t host_cst_cap = 0;
     std::vector<uint8_t> cst_shadow;        // what the device block holds
     // accumulators in one device block (one memset, one copy back), in 64-bit words:
-    // tally[tally_len] | n_events | extrema (2 words) + column histograms | claim counters (2 x uint32 per chunk)
+    // tally[tally_len] | n_events | extrema (2 words) + column histograms | claim counters (4 x uint32 per chunk: ring claim counter, fresh-list length, tail-list length, spare)
     DevBuf<unsigned long long> acc;
     unsigned long long *host_acc = nullptr; // pinned mirror of tally .. column histograms
     size_t host_acc_cap = 0, extras_len = 0, n_case_ev = 0;
     DevBuf<Fresh> fresh;                    // photons that survived their first event (init kernel -> walk kernel)
     DevBuf<RawResult> raw;
+    DevBuf<uint32_t> tail;                  // walk kernel -> tail kernel hand-over list (calls that run alone)
     DevBuf<uint8_t> recs;                   // record columns of one chunk, packed like mc3d_records_layout
     cudaStream_t stream = nullptr;          // each slot has its own stream: two calls in flight overlap on the GPU
     std::vector<cudaEvent_t> ev;            // pairs (begin, end) around walk+finalize of each chunk
@@ -180,6 +182,7 @@ struct mc3d_ctx {
     std::vector<Occupancy> occupancy;   // resident walk-kernel blocks per SM, queried once per variant
     bool input_caching = true; // skip the upload of inputs identical to the slot's previous call
     int drain_give = -1;       // -1 = automatic (16 when other calls are in flight, else off); MC3D_DRAIN_GIVE overrides
+    int tail_kernel = -1;      // -1 = automatic (a call that runs alone finishes in the tail kernel); MC3D_TAIL overrides
     int drain_latency = -1;    // -1 = automatic (on for a call that runs alone); MC3D_DRAIN_LATENCY overrides
     int walk_path = MC3D_PATH_AUTO;   // mc3d_set_walk_path / MC3D_WALK_PATH
     double fused_max_events = 2.5;    // automatic path: fused kernel when a photon is expected to end within this many events
@@ -350,6 +353,8 @@ static void apply_env(mc3d_ctx *ctx)
 {
     const char *e = getenv("MC3D_DRAIN_GIVE");        // experiments only; results do not depend on it
     if (e && *e) ctx->drain_give = std::max(0, std::min(31, atoi(e)));
+    e = getenv("MC3D_TAIL");
+    if (e && *e) ctx->tail_kernel = atoi(e) ? 1 : 0;
     e = getenv("MC3D_DRAIN_LATENCY");
     if (e && *e) ctx->drain_latency = atoi(e) ? 1 : 0;
     e = getenv("MC3D_WALK_PATH");                     // same: "fused" | "persistent" | "auto"
@@ -450,7 +455,7 @@ int mc3d_destroy(mc3d_ctx *ctx)
         if (cudaSetDevice(d.id) != cudaSuccess) continue;
         for (Slot &s : d.slot) {
             if (s.stream) cudaStreamSynchronize(s.stream);
-            s.cst.release(); s.acc.release(); s.fresh.release(); s.raw.release(); s.recs.release();
+            s.cst.release(); s.acc.release(); s.fresh.release(); s.raw.release(); s.tail.release(); s.recs.release();
             if (s.host_cst) cudaFreeHost(s.host_cst);
             if (s.host_acc) cudaFreeHost(s.host_acc);
             for (cudaEvent_t e : s.ev) cudaEventDestroy(e);
@@ -514,6 +519,15 @@ int mc3d_set_walk_path(mc3d_ctx *ctx, int path)
     if (path != MC3D_PATH_AUTO && path != MC3D_PATH_FUSED && path != MC3D_PATH_PERSISTENT)
         return fail(MC3D_EINVAL, "path must be MC3D_PATH_AUTO, MC3D_PATH_FUSED or MC3D_PATH_PERSISTENT");
     ctx->walk_path = path;
+    return MC3D_OK;
+}
+
+int mc3d_set_tail_kernel(mc3d_ctx *ctx, int mode)
+{
+    int rc = check_ctx(ctx);
+    if (rc) return rc;
+    if (mode < -1 || mode > 1) return fail(MC3D_EINVAL, "mode must be -1 (automatic), 0 or 1");
+    ctx->tail_kernel = mode;
     return MC3D_OK;
 }
 
@@ -764,7 +778,7 @@ static int run_job(mc3d_ctx *ctx, int slot_idx, const Job &J)
         s.extras_len = 2 + n_hist;
         s.n_case_ev = n_case_ev;
         const size_t acc_copy = tally_len + 1 + s.extras_len + n_case_ev;          // words copied back
-        const size_t acc_words = acc_copy + (size_t)std::max(n_chunks, 1);        // + one word (2 counters) per chunk
+        const size_t acc_words = acc_copy + 2 * (size_t)std::max(n_chunks, 1);    // + two words (4 counters) per chunk
         const bool cst_moved = s.cst.cap < cst_bytes;
         CUDA_TRY(s.cst.ensure(cst_bytes));
         CUDA_TRY(s.acc.ensure(acc_words));
@@ -905,8 +919,8 @@ static int run_job(mc3d_ctx *ctx, int slot_idx, const Job &J)
                 Wc.c = make_devcase(&hc.params, 0, n_rows);
                 Wc.c.id0 = hc.id_begin + J.range_begin + off + c_off;
             }
-            Wc.counter = d_counters + 2 * c;
-            Wc.n_fresh = d_counters + 2 * c + 1;
+            Wc.counter = d_counters + 4 * c;
+            Wc.n_fresh = d_counters + 4 * c + 1;
             Wc.fresh = s.fresh.p;
             Wc.raw = s.raw.p;
             const int want = (int)((c_cnt + ctx->block_threads - 1) / ctx->block_threads);
@@ -914,7 +928,17 @@ static int run_job(mc3d_ctx *ctx, int slot_idx, const Job &J)
             CUDA_TRY(cudaEventRecord(s.ev[2 * c], s.stream));
             if (!fused) {
                 CUDA_TRY(launch_init(Wc, impurity, d.sm_count, s.stream));
+                // a call that runs alone hands its last photons over to the tail kernel (dense warps, helper lanes)
+                const bool use_tail = ctx->tail_kernel >= 0 ? ctx->tail_kernel != 0 : lone;
+                const int lanes = grid * ctx->block_threads;
+                if (use_tail) {
+                    CUDA_TRY(s.tail.ensure((size_t)TAIL_WORDS * lanes));
+                    Wc.tail = s.tail.p;
+                    Wc.n_tail = d_counters + 4 * c + 2;
+                    Wc.tail_cap = (uint32_t)lanes;
+                }
                 CUDA_TRY(launch_walk(Wc, impurity, ctx->block_threads, bps_variant, grid, s.stream, nullptr));
+                if (use_tail) CUDA_TRY(launch_tail(Wc, impurity, lanes, s.stream));
             }
             FinalizeParams F;
             memset(&F, 0, sizeof F);

@@ -125,7 +125,13 @@ struct WalkParams {
     uint32_t *n_fresh;      // number of entries in `fresh` (appended by the init kernel)
     Fresh *fresh;           // [n_photon]
     RawResult *raw;         // [n_photon]
+    // hand-over to the tail kernel (a call that runs alone; null = the walk kernel drains by itself)
+    uint32_t *tail;         // [TAIL_WORDS][tail_cap]: state of the photons still walking when the fresh list ran out
+    uint32_t *n_tail;       // entries in `tail`
+    uint32_t tail_cap;      // >= lanes of the walk kernel's grid
+    uint32_t pad;
 };
+constexpr int TAIL_WORDS = 11;   // z, ux, uy, uz, path_lo, path_hi, i, plo, phi, row, blk
 
 struct FinalizeParams {
     const RawResult *raw;

@@ -174,6 +174,24 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) walk_kernel(const __grid_co
     // launches in flight the issue slots matter instead: eager group, and the warps consolidate through the block's
     // pool (see DrainPool).
     TIMELINE(1);
+    if (P.tail) {
+        // a call that runs alone: its tail is the dependent chain of its longest walks, and that belongs to a kernel of
+        // its own (tail_kernel.cu: dense warps, helper lanes).  Resolve what is waiting, hand the walking photons over.
+        if (!alive && L.i != 0u) alive = resolve_lane<IMP, SWEEP>(P, cases, rows, rows_addr, L);
+        const uint32_t m = __ballot_sync(0xffffffffu, alive);
+        uint32_t at = 0u;
+        if (lane == 0 && m) at = atomicAdd(P.n_tail, (uint32_t)__popc(m));
+        at = __shfl_sync(0xffffffffu, at, 0) + __popc(m & ((1u << lane) - 1u));
+        if (alive) {
+            uint32_t *t = P.tail + at;
+            const uint32_t cap = P.tail_cap;
+            t[0] = __float_as_uint(L.z); t[cap] = __float_as_uint(L.ux); t[2 * cap] = __float_as_uint(L.uy);
+            t[3 * cap] = __float_as_uint(L.uz); t[4 * cap] = __float_as_uint(L.path_lo); t[5 * cap] = __float_as_uint(L.path_hi);
+            t[6 * cap] = L.i; t[7 * cap] = L.plo; t[8 * cap] = L.phi; t[9 * cap] = lane_row(L, rows_addr); t[10 * cap] = L.blk;
+        }
+        TIMELINE(2);
+        return;
+    }
     if (lane == 0) atomicAdd(&D.draining, 1u);
     const uint32_t give_max = P.drain_give;   // 0: plain drain loop (the launch runs alone)
     // Unlocked peek at the pool: (count << 8) | draining, lane 0's view, so every branch on it is warp-uniform.

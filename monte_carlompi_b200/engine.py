@@ -15,7 +15,7 @@ N_COND = 8
 N_SLOTS = 16
 FLAG_LAMBERT_BOTTOM = 1
 FLAG_LAMBERT_SURFACE = 2
-ABI_VERSION = 3
+ABI_VERSION = 4
 PATH_AUTO, PATH_FUSED, PATH_PERSISTENT = 0, 1, 2
 PACKED_MAX_ROWS = 512          # packed 16-byte records hold the SSP row in 9 bits
 PACKED_NSCAT_MAX = 0x7fffff    # ... and n_scat in 23 bits (saturating; Stats.packed_saturated reports it)
@@ -24,7 +24,7 @@ EXPORTS = ('mc3d_abi_version', 'mc3d_last_error', 'mc3d_query', 'mc3d_create', '
            'mc3d_create_rank', 'mc3d_destroy', 'mc3d_host_alloc', 'mc3d_host_free', 'mc3d_run', 'mc3d_run_async',
            'mc3d_wait', 'mc3d_reduce_tally', 'mc3d_replay', 'mc3d_set_launch', 'mc3d_write_records_text', 'mc3d_py_repr',
            'mc3d_set_histograms', 'mc3d_get_histograms', 'mc3d_records_layout', 'mc3d_set_input_caching',
-           'mc3d_unpack_records', 'mc3d_set_walk_path', 'mc3d_run_sweep', 'mc3d_run_sweep_async')
+           'mc3d_unpack_records', 'mc3d_set_walk_path', 'mc3d_run_sweep', 'mc3d_run_sweep_async', 'mc3d_set_tail_kernel')
 
 
 class Mc3dError(RuntimeError):
@@ -127,6 +127,7 @@ def load_library():
     lib.mc3d_get_histograms.argtypes = [vp, i32, vp, vp, vp]
     lib.mc3d_unpack_records.argtypes = [vp, u64, vp, i32]
     lib.mc3d_set_walk_path.argtypes = [vp, i32]
+    lib.mc3d_set_tail_kernel.argtypes = [vp, i32]
     lib.mc3d_run_sweep.argtypes = [vp, vp, i32, vp, i32, u64, vp, vp, vp, vp]
     lib.mc3d_run_sweep_async.argtypes = [vp, i32, vp, i32, vp, i32, u64, u64, u64, vp, vp, vp]
     if lib.mc3d_abi_version() != ABI_VERSION:
@@ -314,6 +315,11 @@ class Context(object):
         also accepts 'auto' / 'fused' / 'persistent'.  A performance choice: the results are bit-identical."""
         path = {'auto': PATH_AUTO, 'fused': PATH_FUSED, 'persistent': PATH_PERSISTENT}.get(path, path)
         _check(self._lib.mc3d_set_walk_path(self._ctx, int(path)))
+
+    def set_tail_kernel(self, mode=-1):
+        """How a persistent-path call ends: 1 = tail kernel, 0 = the walk kernel drains by itself, -1 = automatic
+        (mc3d_set_tail_kernel).  Results do not depend on it."""
+        _check(self._lib.mc3d_set_tail_kernel(self._ctx, int(mode)))
 
     def set_launch(self, blocks_per_sm=0, block_threads=0, refill_threshold=0):
         _check(self._lib.mc3d_set_launch(self._ctx, blocks_per_sm, block_threads, refill_threshold))

@@ -28,6 +28,10 @@ CONFIGS = {
                Lambertian_reflectance=0.5, fixture='spectral', n_theta_bins=137, base_seed=7000),
     'slab_lb': dict(wvl0=1.3, half_width=0.085, rds_snw=100., theta_0=15., tau_tot=3.0, Lambertian_bottom=True,
                     Lambertian_reflectance=0.5, fixture='spectral', n_theta_bins=137, base_seed=17000),
+    # BASELINE.json configs[3]: visible wavelength, weakly absorbing ice, large grains -- thousands of scatterings per
+    # photon (mean ~2700, walks beyond 10^5 events): the long-walk regime (renormalisation, path accumulation in fp32)
+    'vis': dict(wvl0=0.53, half_width=0.085, rds_snw=1000., theta_0=15., tau_tot=1e6, Lambertian_bottom=True,
+                Lambertian_reflectance=0.5, fixture='const-vis', n_theta_bins=137, base_seed=37000),
     'impurity': dict(wvl0=1.3, half_width=0.085, rds_snw=100., theta_0=30., tau_tot=3.0, imp_cnc=1e-5,
                      Lambertian_bottom=True, Lambertian_reflectance=0.5, fixture='spectral', n_theta_bins=137,
                      base_seed=27000),
@@ -55,8 +59,8 @@ def main():
     CFG.clear()
     CFG.update(CONFIGS[name])
     from monte_carlompi_b200 import ssp_fixtures
-    optics = os.path.join(tempfile.mkdtemp(prefix='mc3d_optics_'), 'spectral')
-    ssp_fixtures.write_optics_dir(optics, 'spectral', (100,))
+    optics = os.path.join(tempfile.mkdtemp(prefix='mc3d_optics_'), CFG['fixture'])
+    ssp_fixtures.write_optics_dir(optics, CFG['fixture'], (int(CFG['rds_snw']),))
     n_chunks = n_proc * 4
     sizes = [len(c) for c in np.array_split(np.arange(n_total), n_chunks)]
     with mp.Pool(n_proc) as pool:
@@ -77,6 +81,8 @@ def main():
     out = os.path.join(ROOT, 'tests', 'golden', 'stats_%s_reference.npz' % name)
     np.savez_compressed(out, config=np.array(repr(dict(CFG, n_photon=n_total))), k_first=k_lo, counts=counts, brf=brf,
                         n_scat_hist=np.bincount(np.minimum(cat['n_scat'], 4095), minlength=4096),
+                        n_scat_sq_sum=(cat['n_scat'].astype(np.float64) ** 2).sum(),
+                        n_scat_log2_hist=np.bincount(np.floor(np.log2(np.maximum(cat['n_scat'], 1))).astype(np.int64), minlength=32),
                         n_scat_sum=cat['n_scat'].sum(), path_sum=cat['path_length'].sum(),
                         path_sq_sum=(cat['path_length'] ** 2).sum(),
                         path_sum_reflected=cat['path_length'][refl].sum())

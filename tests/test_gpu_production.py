@@ -354,11 +354,56 @@ def test_results_do_not_depend_on_range_split_or_launch_shape():
             for col in ref:
                 assert np.array_equal(rec[col], ref[col]), (col, give)
             assert np.array_equal(t, tref) and st2['n_events'] == st['n_events']
+        # (f) how the call ends: the walk kernel draining by itself (latency-oriented groups), or the tail kernel (dense
+        #     warps, then helper lanes preparing a lone photon's next eight events): bit-identical
+        for mode, bps in ((0, 255), (1, 255), (1, 1), (0, 4), (1, 4)):
+            ctx.set_tail_kernel(mode)
+            ctx.set_launch(bps, 256, 4)
+            rec, t, st2 = ctx.run(P, rows, seed, 0, n)
+            for col in ref:
+                assert np.array_equal(rec[col], ref[col]), (col, mode, bps)
+            assert np.array_equal(t, tref) and st2['n_events'] == st['n_events']
     finally:
+        ctx.set_tail_kernel(-1)
         ctx.set_launch(255, 256, 4)      # back to the automatic grid
     # (e) a different seed gives a different realisation
     other, _, _ = ctx.run(P, rows, seed + 1, 0, n)
     assert (other['n_scat'] != ref['n_scat']).mean() > 0.5
+
+
+@pytest.mark.parametrize('what', ['visible_long_walks', 'impurity', 'lambert_bottom_thin', 'tiny'])
+def test_tail_kernel_is_bit_identical(what):
+    """A call that runs alone ends in tail_kernel.cu (helper lanes prepare the next eight events of a warp's last
+    photons).  Same per-photon stream, same arithmetic: identical records, tallies and event counts, also where walks
+    are thousands of events long, where the impurity species is drawn between events (no helpers) and where a
+    Lambertian bottom reflects photons back into the walk."""
+    if what == 'visible_long_walks':
+        rows, n = gpu_util.const_table(0.999989859099, 0.89, ext=6.6), 3000
+        P, _ = gpu_util.both_params(15., 1e6, 0.5, 0.5, SIGMA13, 24, True)
+    elif what == 'impurity':
+        rows, n = gpu_util.fixture_table('spectral', 100, 104, 156, 1e-5), 100000
+        P, _ = gpu_util.both_params(30., 3.0, 0.5, 1.3, SIGMA13, 104, True)
+    elif what == 'lambert_bottom_thin':
+        rows, n = gpu_util.fixture_table('spectral', 100, 64, 116), 100000
+        P, _ = gpu_util.both_params(15., 0.3, 1.0, 0.9, SIGMA13, 64, True)
+    else:
+        rows, n = gpu_util.fixture_table('spectral', 100, 104, 156), 37
+        P, _ = gpu_util.both_params(15., 1e6, 0.5, 1.3, SIGMA13, 104, True)
+    ctx = gpu_util.context()
+    out = {}
+    try:
+        ctx.set_walk_path('persistent')
+        for mode in (0, 1):
+            ctx.set_tail_kernel(mode)
+            out[mode] = ctx.run(P, rows, 5, 1 << 34, n)
+    finally:
+        ctx.set_tail_kernel(-1)
+        ctx.set_walk_path('auto')
+    for col in out[0][0]:
+        assert np.array_equal(out[0][0][col], out[1][0][col]), col
+    assert np.array_equal(out[0][1], out[1][1]) and out[0][2]['n_events'] == out[1][2]['n_events']
+    if what == 'visible_long_walks':
+        assert out[1][0]['n_scat'].max() > 20000
 
 
 @pytest.mark.parametrize('n', [0, 1, 31, 32, 33, 1000])
