@@ -6,6 +6,14 @@
 #include "../../monte_carlompi_b200/csrc/mc3d_device.cuh"
 using namespace mc3d;
 
+// the round-1 generator (ten rounds, one block per event), kept here for the log this file produced
+static __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const uint32_t *__restrict__ rk)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) philox_round(c0, c1, c2, c3, rk[2 * (r % PHILOX_ROUNDS)], rk[2 * (r % PHILOX_ROUNDS) + 1]);
+    return make_uint4(c0, c1, c2, c3);
+}
+
 struct Keys { uint32_t rk[20]; };
 
 template <int MODE>
