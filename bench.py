@@ -47,7 +47,8 @@ WORKLOAD = dict(wvl0=1.3, half_width=0.085, rds_snw=100, theta_0=15.0, tau_tot=1
 CALLS_PER_STEP = 256
 INVARIANCE_PHOTONS = 1000000
 W_EVENT = 111.0   # algorithmic lane-instructions per scattering event
-NCU_TRAFFIC_BYTES_PER_PHOTON = 47.8   # walk kernel, dram read + write per photon, from the ncu --set full capture (profiles/)
+NCU_TRAFFIC_BYTES_PER_PHOTON = 52.0   # walk kernel at the bench's launch size: dram__bytes_read.sum + dram__bytes_write.sum = 34.0 + 18.1 MB per
+                                      # 1e6 photons (profiles/r02_walk_bench_1e6_ncu_summary.csv; algorithmic: 16 B fresh read + 32 B raw written)
 KERNELS_PER_CALL = 3                  # init + walk + finalize
 
 
@@ -510,8 +511,8 @@ def main():
                          'achieved_is': 'events of the timed region / its duration (per GPU), %d calls in flight' % depth,
                          'isolated_call_ms': float(np.mean(iso_ms)), 'isolated_achieved': iso, 'isolated_frac': iso / peak,
                          'traffic': traffic * n if traffic else None,
-                         'traffic_is': 'dram__bytes_read.sum + dram__bytes_write.sum of one call\'s kernels from the ncu --set full capture under '
-                                       'profiles/ (per photon x photons per call)',
+                         'traffic_is': 'dram__bytes_read.sum + dram__bytes_write.sum of the walk kernel (the dominant kernel: 94 % of a call) from the ncu '
+                                       '--set full capture profiles/r02_walk_bench_1e6_ncu_summary.csv, per launch; algorithmic 48 B per photon',
                          'hbm': {'achieved': rec_bytes / (np.mean(iso_ms) * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
                                  'frac': rec_bytes / (np.mean(iso_ms) * 1e-3) / 1e9 / hbm_peak,
                                  'peak_is': 'hbm_gbs of MEASURED_PEAKS.json' if 'hbm_gbs' in peaks else 'fallback 6.65 TB/s',
