@@ -465,7 +465,7 @@ def main():
         peak = stats['sm_count'] * 128 * f_mhz * 1e6 / W_EVENT
         n_calls = args.steps * calls
         ach = events_a / T_a                                   # per GPU, pipelined steady state of this workload
-        iso = float(np.mean(iso_events) / (np.mean(iso_ms) * 1e-3))
+        iso = float(np.median(iso_events) / (np.median(iso_ms) * 1e-3))     # median of 10 calls: one hiccup does not move it
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
@@ -509,12 +509,12 @@ def main():
                          'peak_is': 'N_SM x 128 lanes x f_SM / 111 lane-instructions per event (SURVEY.md 8d); N_SM=%d queried, f_SM=%.0f MHz '
                                     '%s' % (stats['sm_count'], f_mhz, 'median NVML sample under load' if clocks['sm_mhz'] else 'cudaDevAttrClockRate'),
                          'achieved_is': 'events of the timed region / its duration (per GPU), %d calls in flight' % depth,
-                         'isolated_call_ms': float(np.mean(iso_ms)), 'isolated_achieved': iso, 'isolated_frac': iso / peak,
+                         'isolated_call_ms': float(np.median(iso_ms)), 'isolated_achieved': iso, 'isolated_frac': iso / peak,
                          'traffic': traffic * n if traffic else None,
                          'traffic_is': 'dram__bytes_read.sum + dram__bytes_write.sum of the walk kernel (the dominant kernel: 94 % of a call) from the ncu '
                                        '--set full capture profiles/r02_walk_bench_1e6_ncu_summary.csv, per launch; algorithmic 48 B per photon',
-                         'hbm': {'achieved': rec_bytes / (np.mean(iso_ms) * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
-                                 'frac': rec_bytes / (np.mean(iso_ms) * 1e-3) / 1e9 / hbm_peak,
+                         'hbm': {'achieved': rec_bytes / (np.median(iso_ms) * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
+                                 'frac': rec_bytes / (np.median(iso_ms) * 1e-3) / 1e9 / hbm_peak,
                                  'peak_is': 'hbm_gbs of MEASURED_PEAKS.json' if 'hbm_gbs' in peaks else 'fallback 6.65 TB/s',
                                  'achieved_is': 'algorithmic record bytes of one call / isolated call time: the path is not HBM-bound'}},
             'cpu_baseline': cpu,

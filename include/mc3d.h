@@ -277,11 +277,12 @@ int mc3d_py_repr(double x, char *buf);
  * number of waiting lanes at which a warp resolves / refills (default 4).  0 keeps the current value. */
 int mc3d_set_launch(mc3d_ctx *ctx, int blocks_per_sm, int block_threads, int refill_threshold);
 
-/* Which kernels walk the photons.  MC3D_PATH_PERSISTENT: init -> persistent-warp walk -> finalize, per-photon state
- * handed through HBM (made for walks of tens to millions of events).  MC3D_PATH_FUSED: one kernel, one thread per
- * photon from its first draw to its record (made for walks of a few events: strongly absorbing grains, thin slabs,
- * Lambertian_surface).  MC3D_PATH_AUTO (default) picks from the table's single-scattering albedo and tau_tot.  A
- * performance choice only: both follow the same per-photon random stream and return bit-identical results. */
+/* Which kernels walk the photons.  MC3D_PATH_PERSISTENT: init -> persistent-warp walk (-> tail) -> finalize, per-photon
+ * state handed through HBM.  MC3D_PATH_FUSED: one kernel from a photon's first draw to its record, nothing but the
+ * record touches HBM (three full-width stages over shared-memory queues; made for walks of a few events: strongly
+ * absorbing grains, thin slabs, Lambertian_surface).  MC3D_PATH_AUTO (default) picks by the expected walk length --
+ * at present always the persistent path, which measures faster at every walk length.  A performance
+ * choice only: both follow the same per-photon random stream and return bit-identical results. */
 #define MC3D_PATH_AUTO 0
 #define MC3D_PATH_FUSED 1
 #define MC3D_PATH_PERSISTENT 2

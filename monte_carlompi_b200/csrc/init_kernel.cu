@@ -8,8 +8,8 @@
 //     move, direct-transmission / Lambertian-bottom / first-extinction absorption tests (1399-1466)
 //   (all of it in walk_device.cuh: first_event(), shared with the fused kernel)
 //
-// Photons that are still walking after event 1 are appended to the `fresh` list (warp-aggregated append: one
-// atomicAdd per warp); the walk kernel's lanes pick them up from there.  Photons that end on event 1 store their
+// Photons that are still walking after event 1 leave their state in the `fresh` list (entry = photon index; the
+// others are marked dead); the walk kernel's lanes pick them up from there.  Photons that end on event 1 store their
 // raw record here.  Keeping this code out of the walk kernel is what lets the walk kernel run at 48 registers per
 // thread (40 resident warps per SM) without spilling in its event loop.
 #include <algorithm>
@@ -27,51 +27,28 @@ __global__ void __launch_bounds__(BLOCK) init_kernel(const __grid_constant__ Wal
     stage_tables(P, smem_raw, BLOCK);
     __syncthreads();
     const uint32_t rows_addr = shared_address(rows);
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    // One append per BLOCK and iteration (256 photons), not per warp: the list length is a single address, and returning
-    // atomics on one address serialise in L2 at ~1 per ns -- with one per warp that alone took 0.27 ms per 10^7
-    // photons (profiles/r02_persistent_short_walk_launches.csv), several times the kernel's arithmetic.
-    __shared__ uint32_t warp_count[BLOCK / 32];
-    __shared__ uint32_t block_base;
-    // whole blocks iterate together (uniform trip count: the barriers below are executed by every thread)
-    for (uint32_t base = blockIdx.x * BLOCK; base < P.n_photon; base += gridDim.x * BLOCK) {
-        const uint32_t pid = base + threadIdx.x;
-        bool survive = false;
-        uint32_t redo = 0u;
+    // Photon pid's entry of the `fresh` list is fresh[pid]: survivors of event 1 with their state, the others marked
+    // FRESH_DEAD (the walk kernel's lanes skip those when they refill their ring).  No append counter: a list length is a
+    // single address, and returning atomics on one address serialise in L2 at ~1 per ns -- one per warp took 0.27 ms
+    // per 10^7 photons, one per block still stalled every block on its round trip
+    // (profiles/r02_persistent_short_walk_launches.csv).  Coalesced 16-byte stores instead.
+    for (uint32_t pid = blockIdx.x * BLOCK + threadIdx.x; pid < P.n_photon; pid += gridDim.x * BLOCK) {
+        uint32_t redo = 0u, row = 0u;
         float dtau = 0.0f;
-        uint32_t row = 0, lcase = 0;
-        if (pid < P.n_photon) {
-            Lane L;
-            lcase = find_case<SWEEP>(P, cases, pid);
-            const DevCase &C = SWEEP ? cases[lcase] : P.c;
-            const uint64_t id = C.id0 + pid;
-            uint32_t cond = first_event<IMP>(P, C, (uint32_t)(id >> 32), rows, rows_addr, (uint32_t)id, L, row, dtau, redo);
-            // Event 1 needed attention and the photon is still alive (reflected off a Lambertian bottom on its first
-            // step, possibly through event 2 already; or a weakly absorbing row whose coarse key asked for the fine
-            // test / a renormalisation): it is handed over in its state after the MOVE of event 1, with the event's
-            // key and species in Fresh::redo, and the walk kernel's resolve pass redoes the chain of event 1
-            // (deterministic: same blocks, same result)
-            if (cond == ALIVE) survive = true;
-            else store_raw(P, pid, L.ux, L.uy, L.uz, __fadd_rn(L.path_hi, L.path_lo), L.i - 1u, cond, row, lcase);
-        }
-        const uint32_t m = __ballot_sync(0xffffffffu, survive);
-        if (lane == 0) warp_count[warp] = (uint32_t)__popc(m);
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            uint32_t total = 0;
-#pragma unroll
-            for (int w = 0; w < BLOCK / 32; ++w) total += warp_count[w];
-            block_base = total ? atomicAdd(P.n_fresh, total) : 0u;
-        }
-        __syncthreads();
-        if (survive) {
-            uint32_t at = block_base + __popc(m & ((1u << lane) - 1u));
-            for (uint32_t w = 0; w < warp; ++w) at += warp_count[w];
-            Fresh f;
-            f.pid = pid; f.row = row | (lcase << 12); f.dtau = dtau; f.redo = redo;
-            *reinterpret_cast<uint4 *>(P.fresh + at) = *reinterpret_cast<uint4 *>(&f);
-        }
-        __syncthreads();   // warp_count / block_base are rewritten by the next iteration
+        Lane L;
+        const uint32_t lcase = find_case<SWEEP>(P, cases, pid);
+        const DevCase &C = SWEEP ? cases[lcase] : P.c;
+        const uint64_t id = C.id0 + pid;
+        const uint32_t cond = first_event<IMP>(P, C, (uint32_t)(id >> 32), rows, rows_addr, (uint32_t)id, L, row, dtau, redo);
+        // cond == ALIVE with redo != 0: event 1 needed attention and the photon is still alive (reflected off a
+        // Lambertian bottom on its first step, possibly through event 2 already; or a weakly absorbing row whose coarse
+        // key asked for the fine test / a renormalisation): it is handed over in its state after the MOVE of event 1,
+        // with the event's key and species in Fresh::redo, and the walk kernel's resolve pass redoes the chain of event
+        // 1 (deterministic: same blocks, same result)
+        Fresh f;
+        f.pid = pid; f.row = cond == ALIVE ? row | (lcase << 12) : FRESH_DEAD; f.dtau = dtau; f.redo = redo;
+        *reinterpret_cast<uint4 *>(P.fresh + pid) = *reinterpret_cast<uint4 *>(&f);
+        if (cond != ALIVE) store_raw(P, pid, L.ux, L.uy, L.uz, __fadd_rn(L.path_hi, L.path_lo), L.i - 1u, cond, row, lcase);
     }
 }
 

@@ -144,7 +144,7 @@ struct Slot {
     size_t host_cst_cap = 0;
     std::vector<uint8_t> cst_shadow;        // what the device block holds
     // accumulators in one device block (one memset, one copy back), in 64-bit words:
-    // tally[tally_len] | n_events | extrema (2 words) + column histograms | claim counters (4 x uint32 per chunk: ring claim counter, fresh-list length, tail-list length, spare)
+    // tally[tally_len] | n_events | extrema (2 words) + column histograms | claim counters (4 x uint32 per chunk: ring claim counter, spare, tail-list length, spare)
     DevBuf<unsigned long long> acc;
     unsigned long long *host_acc = nullptr; // pinned mirror of tally .. column histograms
     size_t host_acc_cap = 0, extras_len = 0, n_case_ev = 0;
@@ -185,8 +185,10 @@ struct mc3d_ctx {
     int tail_kernel = -1;      // -1 = automatic (a call that runs alone finishes in the tail kernel); MC3D_TAIL overrides
     int drain_latency = -1;    // -1 = automatic (on for a call that runs alone); MC3D_DRAIN_LATENCY overrides
     int walk_path = MC3D_PATH_AUTO;   // mc3d_set_walk_path / MC3D_WALK_PATH
-    double fused_max_events = 2.5;    // automatic path: fused kernel when a photon is expected to end within this many events
-                                      // (measured crossover with the persistent path: profiles/r02_fused_vs_persistent*.log)
+    double fused_max_events = 0.0;    // automatic path: fused kernel when a photon is expected to end within this many events.
+                                      // 0 = never: since the init kernel's fixes the persistent path is faster at every walk
+                                      // length measured, 0.30 vs 0.35 ms per 1e7 photons at 2.1 events each
+                                      // (profiles/r02_fused_vs_persistent.log); MC3D_FUSED_MAX_EVENTS / mc3d_set_walk_path
     std::chrono::steady_clock::time_point t0[N_SLOTS];
     mc3d_stats pending_stats[N_SLOTS];
     bool hist_on = false;
@@ -920,7 +922,6 @@ static int run_job(mc3d_ctx *ctx, int slot_idx, const Job &J)
                 Wc.c.id0 = hc.id_begin + J.range_begin + off + c_off;
             }
             Wc.counter = d_counters + 4 * c;
-            Wc.n_fresh = d_counters + 4 * c + 1;
             Wc.fresh = s.fresh.p;
             Wc.raw = s.raw.p;
             const int want = (int)((c_cnt + ctx->block_threads - 1) / ctx->block_threads);

@@ -78,10 +78,13 @@ struct __align__(16) RawResult {
     uint32_t pad1;
 };
 
-// A photon that survived its first event, waiting for a lane of the walk kernel (written by the init kernel).
+// A photon after its first event, waiting for a lane of the walk kernel (written by the init kernel: entry pid of the
+// list is photon pid of the launch).
+constexpr uint32_t FRESH_DEAD = 0xffffffffu;
 struct __align__(16) Fresh {
     uint32_t pid;    // photon offset in this launch
-    uint32_t row;    // SSP row in the launch's table | (case index in the launch) << 12   (sweep launches)
+    uint32_t row;    // SSP row in the launch's table | (case index in the launch) << 12   (sweep launches);
+                     // FRESH_DEAD: the photon ended on its first event (nothing to walk)
     float dtau;      // free path of the first event
     uint32_t redo;   // != 0: event 1 needed attention and the walk kernel redoes its termination chain (resolve());
                      // key16 << 16 | impurity << 1 | 1 of that event (walk_device.cuh: first_event)
@@ -122,7 +125,6 @@ struct WalkParams {
     const DevRow *rows;     // [n_rows], global
     const DevCase *cases;   // [n_cases], global (sweep launches)
     uint32_t *counter;      // walk kernel: next unclaimed entry of `fresh`
-    uint32_t *n_fresh;      // number of entries in `fresh` (appended by the init kernel)
     Fresh *fresh;           // [n_photon]
     RawResult *raw;         // [n_photon]
     // hand-over to the tail kernel (a call that runs alone; null = the walk kernel drains by itself)

@@ -83,9 +83,10 @@ __device__ __forceinline__ void store_raw(const WalkParams &P, uint32_t pid, flo
                                           float path, uint32_t n_scat, uint32_t cond, uint32_t row, uint32_t lcase)
 {
     RawResult *dst = P.raw + pid;
+    // the whole 32-byte sector is written (two 16-byte stores): a partly written sector makes L2 fetch the rest from
+    // DRAM first (it showed as 16 B of reads per record in the ncu captures)
     *reinterpret_cast<float4 *>(dst) = make_float4(ux, uy, uz, path);
-    if (P.n_cases) *reinterpret_cast<uint4 *>(&dst->n_scat) = make_uint4(n_scat, cond | (row << 8), lcase, 0u);
-    else *reinterpret_cast<uint2 *>(&dst->n_scat) = make_uint2(n_scat, cond | (row << 8));
+    *reinterpret_cast<uint4 *>(&dst->n_scat) = make_uint4(n_scat, cond | (row << 8), lcase, 0u);
 }
 
 // ice or impurity for event i (monte_carlo3D.py:1375-1383); only drawn when an impurity is present
@@ -440,7 +441,12 @@ __device__ __forceinline__ uint32_t first_event(const WalkParams &P, const DevCa
     if (C.lambert_surface) {
         dtau = 0.0f;
         L.z = 0.0f; L.path_lo = 0.0f;
-        return lambert_surface_walk<IMP>(P, C, phi, R, L);
+        // (a copy goes through the out-of-line call: passing L itself would pin the caller's lane state to the stack for
+        // every photon of every mode -- local stores on the common path)
+        Lane T = L;
+        const uint32_t c = lambert_surface_walk<IMP>(P, C, phi, R, T);
+        L = T;
+        return c;
     }
     dtau = free_path(w.z);
     L.z = __fmul_rn(dtau, C.mu0z);

@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) walk_kernel(const __grid_co
     WarpRing &Q = rings[threadIdx.x >> 5];
     uint32_t ring_head = 0, ring_tail = 0;   // warp-uniform, free-running
     const uint32_t threshold = max(1u, min(32u, P.refill_threshold));
-    const uint32_t n_fresh = *P.n_fresh;     // complete: the init kernel ran before this launch
+    const uint32_t n_fresh = P.n_photon;     // one entry per photon of the launch; the ones that ended on event 1 are dead
     // photons claimed per atomicAdd: 32, or 64 / 96 for short walks, where one claim per 32 photons would run into the
     // rate at which L2 serialises returning atomics on one address (~1 per ns)
     const uint32_t claim = max(32u, min(96u, P.claim));
@@ -128,9 +128,13 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) walk_kernel(const __grid_co
                 base = __shfl_sync(0xffffffffu, base, 0);
                 if (base >= n_fresh) { exhausted = true; break; }
                 const uint32_t got = min(claim, n_fresh - base);
-                for (uint32_t k = lane; k < got; k += 32u)
-                    Q.entry[(ring_tail + k) & (RING - 1)] = *reinterpret_cast<const uint4 *>(P.fresh + base + k);
-                ring_tail += got;
+                for (uint32_t k0 = 0u; k0 < got; k0 += 32u) {   // live entries only, compacted by a warp vote
+                    uint4 f = make_uint4(0u, FRESH_DEAD, 0u, 0u);
+                    if (k0 + lane < got) f = *reinterpret_cast<const uint4 *>(P.fresh + base + k0 + lane);
+                    const uint32_t live = __ballot_sync(0xffffffffu, f.y != FRESH_DEAD);
+                    if (f.y != FRESH_DEAD) Q.entry[(ring_tail + __popc(live & ((1u << lane) - 1u))) & (RING - 1)] = f;
+                    ring_tail += __popc(live);
+                }
                 __syncwarp();
             }
             const uint32_t avail = ring_tail - ring_head;
