@@ -293,7 +293,8 @@ int mc3d_set_walk_path(mc3d_ctx *ctx, int path);
  * mode 1: the walk kernel hands those photons to a tail kernel (dense warps; once a warp is down to four photons its
  * idle lanes prepare the photons' next events, which halves the time per event of a lone walk).  mode 0: the walk
  * kernel drains by itself, and draining warps consolidate when other calls are in flight.  mode -1 (default): 1 for a
- * call that starts with no other call in flight on the context, else 0.  A performance choice only: bit-identical
+ * synchronous call (mc3d_run, mc3d_run_sweep) that starts with no other call in flight on the context, else 0 (an
+ * asynchronous call may get company before it ends, and the tail kernel would queue behind it).  A performance choice only: bit-identical
  * results either way. */
 int mc3d_set_tail_kernel(mc3d_ctx *ctx, int mode);
 

@@ -182,7 +182,8 @@ struct mc3d_ctx {
     std::vector<Occupancy> occupancy;   // resident walk-kernel blocks per SM, queried once per variant
     bool input_caching = true; // skip the upload of inputs identical to the slot's previous call
     int drain_give = -1;       // -1 = automatic (16 when other calls are in flight, else off); MC3D_DRAIN_GIVE overrides
-    int tail_kernel = -1;      // -1 = automatic (a call that runs alone finishes in the tail kernel); MC3D_TAIL overrides
+    int tail_kernel = -1;      // -1 = automatic (a synchronous call that runs alone finishes in the tail kernel); MC3D_TAIL overrides
+    bool sync_call = false;    // set by mc3d_run / mc3d_run_sweep around their enqueue
     int drain_latency = -1;    // -1 = automatic (on for a call that runs alone); MC3D_DRAIN_LATENCY overrides
     int walk_path = MC3D_PATH_AUTO;   // mc3d_set_walk_path / MC3D_WALK_PATH
     double fused_max_events = 0.0;    // automatic path: fused kernel when a photon is expected to end within this many events.
@@ -573,6 +574,7 @@ struct Job {
     uint64_t *tally = nullptr;
     uint64_t *case_events = nullptr;      // [cases.size()] or null (sweeps)
     int n_theta_bins = 0, n_phi_bins = 0;
+    bool sync = false;                    // issued by mc3d_run / mc3d_run_sweep: nothing else can be enqueued before it ends
 };
 
 DevCase make_devcase(const mc3d_params *P, int row_begin, int n_rows)
@@ -633,6 +635,7 @@ int mc3d_run_async(mc3d_ctx *ctx, int slot_idx, const mc3d_params *P, const mc3d
     J.range_begin = 0; J.range_count = n_photon;
     J.rec = rec; J.tally = tally;
     J.n_theta_bins = P->n_theta_bins; J.n_phi_bins = P->n_phi_bins;
+    J.sync = ctx->sync_call;
     return start_job(ctx, slot_idx, J);
 }
 
@@ -677,6 +680,7 @@ int mc3d_run_sweep_async(mc3d_ctx *ctx, int slot_idx, const mc3d_sweep_case *cas
         return fail(MC3D_EINVAL, "photon range [%llu, +%llu) outside the sweep's %llu photons", (unsigned long long)range_begin,
                     (unsigned long long)range_count, (unsigned long long)total);
     J.range_begin = range_begin; J.range_count = range_count;
+    J.sync = ctx->sync_call;
     return start_job(ctx, slot_idx, J);
 }
 
@@ -686,7 +690,9 @@ int mc3d_run_sweep(mc3d_ctx *ctx, const mc3d_sweep_case *cases, int n_cases, con
     if (stats) memset(stats, 0, sizeof *stats);
     uint64_t total = 0;
     for (int c = 0; cases && c < n_cases; ++c) total += cases[c].n_photon;
+    if (check_ctx(ctx) == MC3D_OK) ctx->sync_call = true;
     int rc = mc3d_run_sweep_async(ctx, 0, cases, n_cases, table, n_rows_total, seed, 0, total, rec, tally, case_events);
+    if (check_ctx(ctx) == MC3D_OK) ctx->sync_call = false;
     if (rc) return rc;
     return mc3d_wait(ctx, 0, stats);
 }
@@ -903,6 +909,11 @@ static int run_job(mc3d_ctx *ctx, int slot_idx, const Job &J)
             resident = per_sm;
         }
         st.grid_blocks = d.sm_count * resident;
+        // a synchronous call that runs alone hands its last photons over to the tail kernel (dense warps, helper lanes).
+        // (Only a synchronous call is known to stay alone: the tail kernel's blocks could not become resident behind the
+        // persistent grids of calls enqueued after an asynchronous one, and its stream would stall.)
+        const bool use_tail = !fused && (ctx->tail_kernel >= 0 ? ctx->tail_kernel != 0 : (lone && J.sync));
+        if (use_tail) CUDA_TRY(s.tail.ensure((size_t)TAIL_WORDS * st.grid_blocks * ctx->block_threads));   // (before the timed span)
 
         size_t case_at = 0;
         for (int c = 0; c < n_chunks; ++c) {
@@ -929,11 +940,8 @@ static int run_job(mc3d_ctx *ctx, int slot_idx, const Job &J)
             CUDA_TRY(cudaEventRecord(s.ev[2 * c], s.stream));
             if (!fused) {
                 CUDA_TRY(launch_init(Wc, impurity, d.sm_count, s.stream));
-                // a call that runs alone hands its last photons over to the tail kernel (dense warps, helper lanes)
-                const bool use_tail = ctx->tail_kernel >= 0 ? ctx->tail_kernel != 0 : lone;
                 const int lanes = grid * ctx->block_threads;
                 if (use_tail) {
-                    CUDA_TRY(s.tail.ensure((size_t)TAIL_WORDS * lanes));
                     Wc.tail = s.tail.p;
                     Wc.n_tail = d_counters + 4 * c + 2;
                     Wc.tail_cap = (uint32_t)lanes;
@@ -1092,7 +1100,9 @@ int mc3d_run(mc3d_ctx *ctx, const mc3d_params *params, const mc3d_ssp_row *table
              uint64_t photon_begin, uint64_t n_photon, const mc3d_records *records, uint64_t *tally,
              mc3d_stats *stats)
 {
+    if (check_ctx(ctx) == MC3D_OK) ctx->sync_call = true;
     int rc = mc3d_run_async(ctx, 0, params, table, n_rows, seed, photon_begin, n_photon, records, tally, stats);
+    if (check_ctx(ctx) == MC3D_OK) ctx->sync_call = false;
     if (rc) return rc;
     return mc3d_wait(ctx, 0, stats);
 }

@@ -355,28 +355,47 @@ class Context(object):
         return ns, pl
 
     # ---- production mode ------------------------------------------------------------------------------------
+    @staticmethod
+    def _records_struct(records, n_photon):
+        if isinstance(records, RecordBuffers):
+            return records.struct_for(n_photon)
+        if isinstance(records, np.ndarray):        # packed records into a caller-owned uint32 array
+            assert records.dtype == np.uint32 and records.flags.c_contiguous and records.size >= 4 * int(n_photon)
+            return Records(None, None, None, None, None, None, records.ctypes.data)
+        if records is not None:
+            return Records(*[records[name].ctypes.data if records.get(name) is not None else None
+                             for name, _ in RECORD_COLUMNS], None)
+        return None
+
     def run_async(self, slot, params, table, seed, photon_begin, n_photon, records=None, tally=None):
-        """Enqueue one walk.  ``records``: RecordBuffers, dict of numpy columns, or None.  ``tally``: uint64 array
-        of shape (n_rows, params.tally_width) or None.  Buffers must stay alive until ``wait(slot)``."""
+        """Enqueue one walk.  ``records``: RecordBuffers, packed uint32 array, dict of numpy columns, or None.
+        ``tally``: uint64 array of shape (n_rows, params.tally_width) or None.  Buffers must stay alive until
+        ``wait(slot)``."""
         if not 0 <= int(slot) < N_SLOTS:
             raise Mc3dError('slot must be in [0, %d)' % N_SLOTS)
         table = np.ascontiguousarray(table, dtype=ROW_DTYPE)
-        rec_struct = None
-        if isinstance(records, RecordBuffers):
-            rec_struct = records.struct_for(n_photon)
-        elif isinstance(records, np.ndarray):      # packed records into a caller-owned uint32 array
-            assert records.dtype == np.uint32 and records.flags.c_contiguous and records.size >= 4 * int(n_photon)
-            rec_struct = Records(None, None, None, None, None, None, records.ctypes.data)
-        elif records is not None:
-            rec_struct = Records(*[records[name].ctypes.data if records.get(name) is not None else None
-                                   for name, _ in RECORD_COLUMNS], None)
+        rec_struct = self._records_struct(records, n_photon)
         if tally is not None:
             assert tally.dtype == np.uint64 and tally.flags.c_contiguous
             assert tally.size == len(table) * params.tally_width
         self._keep[slot] = (params, table, rec_struct, records, tally)
-        _check(self._lib.mc3d_run_async(self._ctx, slot, C.byref(params), _ptr(table), len(table), int(seed),
+        _check(self._lib.mc3d_run_async(self._ctx, int(slot), C.byref(params), _ptr(table), len(table), int(seed),
                                         int(photon_begin), int(n_photon),
                                         C.byref(rec_struct) if rec_struct is not None else None, _ptr(tally), None))
+
+    def run_sync(self, params, table, seed, photon_begin, n_photon, records=None, tally=None):
+        """One walk, start to finish (mc3d_run: slot 0); same arguments as ``run_async``, returns the stats dict.  A
+        synchronous call that finds the context idle ends in the tail kernel (include/mc3d.h: mc3d_set_tail_kernel)."""
+        table = np.ascontiguousarray(table, dtype=ROW_DTYPE)
+        rec_struct = self._records_struct(records, n_photon)
+        if tally is not None:
+            assert tally.dtype == np.uint64 and tally.flags.c_contiguous
+            assert tally.size == len(table) * params.tally_width
+        st = Stats()
+        _check(self._lib.mc3d_run(self._ctx, C.byref(params), _ptr(table), len(table), int(seed), int(photon_begin),
+                                  int(n_photon), C.byref(rec_struct) if rec_struct is not None else None, _ptr(tally),
+                                  C.byref(st)))
+        return st.as_dict()
 
     def run_sweep_async(self, slot, cases, table, seed, records=None, tally=None, case_events=None, range_begin=0,
                         range_count=None):
@@ -426,8 +445,7 @@ class Context(object):
             rec = {name: np.empty(total, dtype=dt) for name, dt in RECORD_COLUMNS}
         t = np.zeros((len(table), cases[0][0].tally_width), np.uint64) if tally else None
         ev = np.zeros(len(cases), np.uint64)
-        self.run_sweep_async(0, cases, table, seed, rec, t, ev)
-        stats = self.wait(0)
+        stats = self._run_sweep_sync(cases, table, seed, rec, t, ev)
         per_case = None
         if records:
             if packed and stats['packed_saturated']:
@@ -437,14 +455,29 @@ class Context(object):
             per_case = [{k: v[edges[i]:edges[i + 1]] for k, v in cols.items()} for i in range(len(cases))]
         return per_case, t, ev, stats
 
+    def _run_sweep_sync(self, cases, table, seed, records, tally, case_events):
+        """The whole sweep, start to finish (mc3d_run_sweep); returns the stats dict."""
+        table = np.ascontiguousarray(table, dtype=ROW_DTYPE)
+        arr = (SweepCase * len(cases))()
+        total = 0
+        for k, (prm, row_begin, n_rows, n) in enumerate(cases):
+            arr[k].params = prm
+            arr[k].row_begin, arr[k].n_rows, arr[k].n_photon = int(row_begin), int(n_rows), int(n)
+            total += int(n)
+        rec_struct = self._records_struct(records, total)
+        st = Stats()
+        _check(self._lib.mc3d_run_sweep(self._ctx, arr, len(cases), _ptr(table), len(table), int(seed),
+                                        C.byref(rec_struct) if rec_struct is not None else None, _ptr(tally),
+                                        _ptr(case_events), C.byref(st)))
+        return st.as_dict()
+
     def _sweep_columns(self, cases, table, seed, tally):
         """A sweep whose packed records saturated (a walk beyond 2^23 scatterings): fetch the six columns instead."""
         total = sum(int(c[3]) for c in cases)
         rec = {name: np.empty(total, dtype=dt) for name, dt in RECORD_COLUMNS}
         t = np.zeros((len(table), cases[0][0].tally_width), np.uint64) if tally else None
         ev = np.zeros(len(cases), np.uint64)
-        self.run_sweep_async(0, cases, table, seed, rec, t, ev)
-        stats = self.wait(0)
+        stats = self._run_sweep_sync(cases, table, seed, rec, t, ev)
         edges = np.cumsum([0] + [int(c[3]) for c in cases])
         return [{k: v[edges[i]:edges[i + 1]] for k, v in rec.items()} for i in range(len(cases))], t, ev, stats
 
@@ -465,8 +498,7 @@ class Context(object):
         elif records:
             rec = {name: np.empty(n_photon, dtype=dt) for name, dt in RECORD_COLUMNS}
         t = np.zeros((len(table), params.tally_width), np.uint64) if tally else None
-        self.run_async(0, params, table, seed, photon_begin, n_photon, rec, t)
-        stats = self.wait(0)
+        stats = self.run_sync(params, table, seed, photon_begin, n_photon, rec, t)
         if packed:
             if stats['packed_saturated']:      # a walk longer than 2^23 events: fetch the columns instead
                 return self.run(params, table, seed, photon_begin, n_photon, records='columns', tally=tally)

@@ -262,13 +262,11 @@ class MonteCarlo(object):
                 if self._rec_buf is not None:
                     self._rec_buf.free()
                 self._rec_buf = engine.RecordBuffers(max(count, 1))
-            ctx.run_async(0, params, table, seed, begin, count, self._rec_buf, tally)
-            stats = ctx.wait(0)
+            stats = ctx.run_sync(params, table, seed, begin, count, self._rec_buf, tally)
             if not stats['packed_saturated']:
                 return self._rec_buf.view(count), stats
         records = {name: np.empty(count, dtype=dt) for name, dt in engine.RECORD_COLUMNS}
-        ctx.run_async(0, params, table, seed, begin, count, records, tally)
-        return records, ctx.wait(0)
+        return records, ctx.run_sync(params, table, seed, begin, count, records, tally)
 
     # ---- sweeps (reference monte_carlo3D-run.py:60-96, 112-122: one run() per wavelength / grain size / angle) -------
     SWEEP_MAX_ROWS = 640            # rows of a batch's concatenated table (40 KB of shared memory per block)
@@ -434,8 +432,7 @@ class MonteCarlo(object):
         begin, count = par._map(n_photon)
         ctx = par.open()
         ctx.set_histograms()
-        ctx.run_async(0, params, table, self.last_seed, begin, count, None, None)
-        ctx.wait(0)
+        ctx.run_sync(params, table, self.last_seed, begin, count, None, None)
         ext = np.array(ctx.extrema(0) if count else (2**32 - 1, 0, np.inf, 0.), np.float64)
         parts = [np.frombuffer(b, np.float64) for b in par.allgather_bytes(ext.tobytes())]
         ns_lo, ns_hi = min(p[0] for p in parts), max(p[1] for p in parts)
@@ -446,8 +443,7 @@ class MonteCarlo(object):
             pl_lo, pl_hi = pl_lo - 0.5, pl_hi + 0.5
         ctx.set_histograms(n_scat_bins, (ns_lo, ns_hi), path_length_bins, (pl_lo, pl_hi), 100.)
         try:
-            ctx.run_async(0, params, table, self.last_seed, begin, count, None, None)
-            self.last_stats = ctx.wait(0)
+            self.last_stats = ctx.run_sync(params, table, self.last_seed, begin, count, None, None)
             ns, pl = ctx.histograms(0)
         finally:
             ctx.set_histograms()

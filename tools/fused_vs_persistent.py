@@ -24,14 +24,12 @@ for wvl0, r, th in ((1.3, 50, 0.), (1.3, 250, 30.), (1.3, 1000, 0.), (1.7, 50, 0
             best = None
             for rep in range(3):
                 t = np.zeros((len(rows), P.tally_width), np.uint64)
-                ctx.run_async(0, P, rows, 20190603, 0, n, buf if records else None, t)
-                st = ctx.wait(0)
+                st = ctx.run_sync(P, rows, 20190603, 0, n, buf if records else None, t)
                 best = st['kernel_ms'] if best is None else min(best, st['kernel_ms'])
             out[path, records] = (best, t.copy(), buf.packed(n).copy() if records else None, st['n_events'])
     ctx.set_walk_path('auto')
     t = np.zeros((len(rows), P.tally_width), np.uint64)
-    ctx.run_async(0, P, rows, 20190603, 0, n, None, t)
-    auto = ctx.wait(0)['walk_path']
+    auto = ctx.run_sync(P, rows, 20190603, 0, n, None, t)['walk_path']
     same = np.array_equal(out['fused', True][1], out['persistent', True][1]) and np.array_equal(out['fused', True][2], out['persistent', True][2])
     print('wvl0=%.1f r=%-4d theta0=%-3d %10.1f | %8.3f / %8.3f  (x%.2f)    | %8.3f / %8.3f  (x%.2f)    | %s %s' % (
         wvl0, r, th, out['fused', False][3] / n, out['fused', False][0], out['persistent', False][0],
