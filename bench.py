@@ -47,8 +47,9 @@ WORKLOAD = dict(wvl0=1.3, half_width=0.085, rds_snw=100, theta_0=15.0, tau_tot=1
 CALLS_PER_STEP = 256
 INVARIANCE_PHOTONS = 1000000
 W_EVENT = 111.0   # algorithmic lane-instructions per scattering event
-NCU_TRAFFIC_BYTES_PER_PHOTON = 52.0   # walk kernel at the bench's launch size: dram__bytes_read.sum + dram__bytes_write.sum = 34.0 + 18.1 MB per
-                                      # 1e6 photons (profiles/r02_walk_bench_1e6_ncu_summary.csv; algorithmic: 16 B fresh read + 32 B raw written)
+NCU_TRAFFIC_BYTES_PER_PHOTON = 16.1   # walk kernel at the bench's launch size: dram__bytes_read.sum + dram__bytes_write.sum = 16.05 + 0.07 MB per
+                                      # 1e6 photons (profiles/r02_walk_bench_1e6_ncu_summary.csv): the 16 B/photon fresh list is read from DRAM,
+                                      # the 32 B/photon raw records stay in the 126 MB L2 until the finalize kernel reads them (algorithmic: 48 B)
 KERNELS_PER_CALL = 3                  # init + walk + finalize
 
 
@@ -512,7 +513,8 @@ def main():
                          'isolated_call_ms': float(np.median(iso_ms)), 'isolated_achieved': iso, 'isolated_frac': iso / peak,
                          'traffic': traffic * n if traffic else None,
                          'traffic_is': 'dram__bytes_read.sum + dram__bytes_write.sum of the walk kernel (the dominant kernel: 94 % of a call) from the ncu '
-                                       '--set full capture profiles/r02_walk_bench_1e6_ncu_summary.csv, per launch; algorithmic 48 B per photon',
+                                       '--set full capture profiles/r02_walk_bench_1e6_ncu_summary.csv, per launch; algorithmic 16 B read + 32 B written per photon, '
+                                       'the written records stay in L2 until the finalize kernel reads them',
                          'hbm': {'achieved': rec_bytes / (np.median(iso_ms) * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
                                  'frac': rec_bytes / (np.median(iso_ms) * 1e-3) / 1e9 / hbm_peak,
                                  'peak_is': 'hbm_gbs of MEASURED_PEAKS.json' if 'hbm_gbs' in peaks else 'fallback 6.65 TB/s',

@@ -184,6 +184,7 @@ struct mc3d_ctx {
     int drain_give = -1;       // -1 = automatic (16 when other calls are in flight, else off); MC3D_DRAIN_GIVE overrides
     int tail_kernel = -1;      // -1 = automatic (a synchronous call that runs alone finishes in the tail kernel); MC3D_TAIL overrides
     bool sync_call = false;    // set by mc3d_run / mc3d_run_sweep around their enqueue
+    int per_lane = 0;          // photons per lane the automatic grid aims for (0 = 26, or 13 for a call that runs alone); MC3D_PER_LANE
     int drain_latency = -1;    // -1 = automatic (on for a call that runs alone); MC3D_DRAIN_LATENCY overrides
     int walk_path = MC3D_PATH_AUTO;   // mc3d_set_walk_path / MC3D_WALK_PATH
     double fused_max_events = 0.0;    // automatic path: fused kernel when a photon is expected to end within this many events.
@@ -356,6 +357,8 @@ static void apply_env(mc3d_ctx *ctx)
 {
     const char *e = getenv("MC3D_DRAIN_GIVE");        // experiments only; results do not depend on it
     if (e && *e) ctx->drain_give = std::max(0, std::min(31, atoi(e)));
+    e = getenv("MC3D_PER_LANE");                      // experiments only
+    if (e && *e) ctx->per_lane = std::max(0, atoi(e));
     e = getenv("MC3D_TAIL");
     if (e && *e) ctx->tail_kernel = atoi(e) ? 1 : 0;
     e = getenv("MC3D_DRAIN_LATENCY");
@@ -903,7 +906,7 @@ static int run_job(mc3d_ctx *ctx, int slot_idx, const Job &J)
             return fail(MC3D_ECUDA, "walk kernel does not fit on an SM (block %d, rows %d, cases %u)", ctx->block_threads, n_rows, max_chunk_cases);
         resident = std::max(1, std::min(resident, bps_variant));
         if (ctx->blocks_per_sm == 0) {
-            const uint64_t per_lane = lone ? 13 : 26;
+            const uint64_t per_lane = ctx->per_lane > 0 ? (uint64_t)ctx->per_lane : (lone ? 13 : 26);
             const uint64_t want_blocks = (std::min<uint64_t>(cnt, CHUNK_PHOTONS) / per_lane + ctx->block_threads - 1) / ctx->block_threads;
             const int per_sm = (int)std::min<uint64_t>(resident, std::max<uint64_t>(1, want_blocks / d.sm_count));
             resident = per_sm;
