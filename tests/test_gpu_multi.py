@@ -100,6 +100,20 @@ h = mc.histograms(200001, 1.3, 0.085, 100., theta_0=15., Lambertian_reflectance=
 if h is not None:
     np.savez(os.path.join(work, 'hist.npz'), ns=h['n_scat'][0], pl=h['path_length_cm'][0], tally=mc.last_tally)
 mc.close()
+# a second instance in the same job (its own rendezvous), no seed given: rank 0's is shared with the other ranks;
+# a sweep of three cases (two of them sharing their rows) over the ranks
+mc2 = monte_carlo3D.MonteCarlo(optics_dir=optics, output_dir=os.path.join(work, 'out2'), tau_tot=6.0)
+cases = [dict(n_photon=50001, wvl0=1.3, half_width=0.085, rds_snw=100., theta_0=15., Lambertian_reflectance=0.5),
+         dict(n_photon=30000, wvl0=1.55, half_width=0.130, rds_snw=250., theta_0=0., Lambertian_reflectance=0.5),
+         dict(n_photon=20002, wvl0=1.3, half_width=0.085, rds_snw=100., theta_0=60., Lambertian_reflectance=0.5)]
+res = mc2.run_sweep(cases, write_output=False)
+rank = int(os.environ.get('RANK', 0))
+with open(os.path.join(work, 'seed.%d' % rank), 'w') as f:
+    f.write(str(mc2.last_seed))
+if res[0] is not None:
+    np.savez(os.path.join(work, 'sweep.npz'), seed=np.uint64(mc2.last_seed),
+             **{'n_scat_%d' % k: r[0]['n_scat'] for k, r in enumerate(res)}, **{'tally_%d' % k: r[1] for k, r in enumerate(res)})
+mc2.close()
 '''
 
 
@@ -137,3 +151,25 @@ def test_driver_one_process_per_gpu_equals_one_process(tmp_path, optics_root):
     assert outs[1][0] == outs[2][0]                                                # byte-identical output file
     for k in ('ns', 'pl', 'tally'):
         assert np.array_equal(outs[1][1][k], outs[2][1][k]), k
+    # the second instance: both ranks walked rank 0's seed, and the two-rank sweep is what one process computes under it
+    w2 = tmp_path / 'w2'
+    assert open(str(w2 / 'seed.0')).read() == open(str(w2 / 'seed.1')).read()
+    z = np.load(str(w2 / 'sweep.npz'))
+    sys.path.insert(0, root)
+    from monte_carloMPI import monte_carlo3D
+    cwd, argv = os.getcwd(), sys.argv
+    os.chdir(str(tmp_path / 'w1'))
+    sys.argv = ['monte_carlo3D-run.py']                       # MonteCarlo() reads flags from the command line
+    try:
+        mc = monte_carlo3D.MonteCarlo(optics_dir=optics_root['spectral'], output_dir=str(tmp_path / 'o3'), tau_tot=6.0, devices=[0])
+        cases = [dict(n_photon=50001, wvl0=1.3, half_width=0.085, rds_snw=100., theta_0=15., Lambertian_reflectance=0.5),
+                 dict(n_photon=30000, wvl0=1.55, half_width=0.130, rds_snw=250., theta_0=0., Lambertian_reflectance=0.5),
+                 dict(n_photon=20002, wvl0=1.3, half_width=0.085, rds_snw=100., theta_0=60., Lambertian_reflectance=0.5)]
+        res = mc.run_sweep(cases, write_output=False, seed=int(z['seed']))
+        mc.close()
+    finally:
+        os.chdir(cwd)
+        sys.argv = argv
+    for k, r in enumerate(res):
+        assert np.array_equal(z['n_scat_%d' % k], r[0]['n_scat']), k
+        assert np.array_equal(z['tally_%d' % k], r[1]), k
