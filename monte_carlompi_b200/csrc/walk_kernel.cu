@@ -16,15 +16,19 @@
 //     raw record) and the empty ones pop a fresh photon from a per-warp shared-memory ring.  The ring is refilled
 //     32 (short walks: 96) photons per atomicAdd (warp-aggregated by construction) with coalesced 512-byte loads from the
 //     `fresh` list the init kernel wrote (wavelength draw, SSP row and the deflection-free first event,
-//     monte_carlo3D.py:1232-1237, happen there).  So the divergent part of a refill is a handful of
-//     shared-memory loads, and walk-length divergence is bounded by the threshold instead of by the longest
-//     walk in the warp.  Nothing heavy is inlined next to the event loop: no spills at 48-56 registers.
-//   * when the id range is exhausted the warp drops into a drain loop that resolves lanes immediately.  Draining
-//     warps empty out exponentially (a warp would run ~4 mean walk lengths for its last lane).  When other
-//     launches share the GPU (the host sets P.drain_give then) they consolidate through a small per-block pool in
-//     shared memory: a warp with few photons left hands them (nine words of state each) to the pool and exits,
-//     warps with free lanes take them over, so the issue slots go to the co-resident launches instead of to
-//     mostly-empty warps.  A launch that runs alone skips this: there it would only add latency.
+//     monte_carlo3D.py:1232-1237, happen there; entry pid is photon pid, the ones that ended on their first event
+//     are marked dead and dropped by a warp vote as the ring is filled).  So the divergent part of a refill is a
+//     handful of shared-memory loads, and walk-length divergence is bounded by the threshold instead of by the
+//     longest walk in the warp.  Nothing heavy is inlined next to the event loop: no spills at 64 registers.
+//   * when the id range is exhausted, what the warp does with the photons it still carries depends on the call:
+//       - a synchronous call that runs alone: its tail is the dependent chain of its longest walks.  The lanes hand
+//         their photons to the tail kernel (tail_kernel.cu: dense warps, helper lanes) and leave;
+//       - other launches share the GPU (the host sets P.drain_give): the warp drains by itself, and since draining
+//         warps empty out exponentially (a warp would run ~4 mean walk lengths for its last lane) they consolidate
+//         through a small per-block pool in shared memory: a warp with few photons left hands them (eleven words of
+//         state each) to the pool and exits, warps with free lanes take them over, so the issue slots go to the
+//         co-resident launches instead of to mostly-empty warps;
+//       - an asynchronous call that happens to start alone: drains by itself with the latency-oriented group.
 //   * angles, records and tallies are produced from the raw records by the coalesced finalize kernel
 //     (finalize_kernel.cu).
 //   * per-photon results depend only on (seed, photon id): bit-identical for any grid, block or GPU count.
