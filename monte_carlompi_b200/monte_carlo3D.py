@@ -293,6 +293,9 @@ class MonteCarlo(object):
         cases = [dict(c) for c in cases]
         if not cases:
             return []
+        if len(cases) > engine.SWEEP_MAX_CASES:
+            raise ValueError('run_sweep takes at most %d cases per call (the case index is part of the photon id): split '
+                             'the sweep' % engine.SWEEP_MAX_CASES)
         if seed is None:
             seed = self.seed
         if seed is None:

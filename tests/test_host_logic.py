@@ -374,3 +374,14 @@ def test_packed_records_unpack_on_the_host():
                            ('path_length', path)):
             assert out[name].dtype == want.dtype and np.array_equal(out[name], want), name
     assert engine.unpack_records(np.zeros(0, np.uint32))['condition'].size == 0
+
+
+def test_run_sweep_rejects_too_many_cases(run_dir, monkeypatch):
+    # the case index lives in the high bits of the photon id and the engine numbers at most 1024 cases per call
+    from monte_carloMPI import monte_carlo3D
+    from monte_carlompi_b200 import engine
+    mc = monte_carlo3D.MonteCarlo()
+    cases = [dict(n_photon=10, wvl0=1.3, half_width=0.085, rds_snw=100.)] * (engine.SWEEP_MAX_CASES + 1)
+    with pytest.raises(ValueError, match='at most'):
+        mc.run_sweep(cases)
+    assert mc.run_sweep([]) == []
